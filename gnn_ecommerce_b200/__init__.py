@@ -1,0 +1,24 @@
+"""gnn_ecommerce_b200 -- B200-native LightGCN hot path (propagation, BPR step, top-k scoring)
+behind the `LightGCN` module API of happykygo/GNN-eCommerce (`src/lightgcn.py`).
+
+Python/PyTorch is plumbing only (device memory, streams, autograd glue); the arithmetic is in
+hand-written sm_100a CUDA behind the C ABI of `include/lgc_b200.h` (`liblgc_b200.so`).
+Importing the package does not load CUDA; the first kernel call does, and fails loudly when the
+library has not been built.
+"""
+from . import synth  # noqa: F401  (numpy only)
+
+__all__ = ["LightGCN", "LGConv", "BPRLoss", "FusedBPRTrainer", "SeenLists", "score_topk", "synth"]
+
+
+def __getattr__(name):
+    if name in ("LightGCN", "LGConv", "BPRLoss"):
+        from . import lightgcn
+        return getattr(lightgcn, name)
+    if name == "FusedBPRTrainer":
+        from .trainer import FusedBPRTrainer
+        return FusedBPRTrainer
+    if name in ("SeenLists", "score_topk"):
+        from . import scoring
+        return getattr(scoring, name)
+    raise AttributeError(name)

@@ -1,0 +1,218 @@
+// Fused BPR step pieces: pair scores, loss + gradients, dense Adam.
+// Replaces the ATen chain of src/lightgcn.py:123-125 (gather, mul, reduce), :279-286
+// (logsigmoid mean), src/utils_v2.py:193-211 (layer-0 L2 term), their autograd backward
+// (src/train_lightgcn.py:146) and torch.optim.Adam (src/train_lightgcn.py:58,147).
+#include "spmm.cuh"
+
+namespace lgc {
+namespace {
+
+constexpr int kMaxVecPerLane = 2;  // ld <= 256 floats
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+__global__ void k_pair_scores(const float* __restrict__ out, int ld, const int64_t* __restrict__ pairs,
+                              int64_t n_pairs, float* __restrict__ score) {
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= n_pairs) return;
+  const float* a = out + (size_t)pairs[j] * ld;
+  const float* b = out + (size_t)pairs[n_pairs + j] * ld;
+  float s = 0.f;
+  for (int c = lane; c < ld / 4; c += 32) s += dot4(ldg_f4(a + 4 * c), ldg_f4(b + 4 * c));
+  s = warp_sum(s);
+  if (lane == 0) score[j] = s;
+}
+
+// One warp per (user, pos, neg) triple.
+__global__ void k_bpr(int64_t num_nodes, int ld, int64_t batch, const int64_t* __restrict__ users,
+                      const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+                      const float* __restrict__ out, const float* __restrict__ e0, float inv_batch,
+                      float decay_over_batch, float alpha0, float* __restrict__ grad_out,
+                      float* __restrict__ grad_e0, int32_t* __restrict__ touched,
+                      float* __restrict__ per_triple, int* __restrict__ bad) {
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= batch) return;
+  const int64_t u = users[t], p = pos[t], n = neg[t];
+  if (u < 0 || u >= num_nodes || p < 0 || p >= num_nodes || n < 0 || n >= num_nodes) {
+    if (lane == 0) { atomicExch(bad, 1); per_triple[2 * t] = 0.f; per_triple[2 * t + 1] = 0.f; }
+    if (touched && lane < 3) touched[3 * t + lane] = 0;
+    return;
+  }
+  const int vec = ld / 4;
+  float4 ou[kMaxVecPerLane], op[kMaxVecPerLane], on[kMaxVecPerLane];
+  float sp = 0.f, sn = 0.f, sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < vec) {
+      ou[k] = ldg_f4(out + (size_t)u * ld + 4 * c);
+      op[k] = ldg_f4(out + (size_t)p * ld + 4 * c);
+      on[k] = ldg_f4(out + (size_t)n * ld + 4 * c);
+      sp += dot4(ou[k], op[k]);
+      sn += dot4(ou[k], on[k]);
+      float4 a = ldg_f4(e0 + (size_t)u * ld + 4 * c), b = ldg_f4(e0 + (size_t)p * ld + 4 * c),
+             d = ldg_f4(e0 + (size_t)n * ld + 4 * c);
+      sq += dot4(a, a) + dot4(b, b) + dot4(d, d);
+    }
+  }
+  sp = warp_sum(sp); sn = warp_sum(sn); sq = warp_sum(sq);
+  const float x = sp - sn;                                    // s+ - s-
+  // -logsigmoid(x) = softplus(-x) = max(-x, 0) + log1p(exp(-|x|))
+  const float loss = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+  const float sig = 1.f / (1.f + expf(x));                    // sigmoid(-x)
+  const float coef = -sig * inv_batch;                        // d loss / d s+  (= - d loss / d s-)
+  if (lane == 0) { per_triple[2 * t] = loss; per_triple[2 * t + 1] = sq; }
+  if (touched && lane < 3) touched[3 * t + lane] = (int32_t)(lane == 0 ? u : (lane == 1 ? p : n));
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < vec) {
+      float4 gu = make_float4(coef * (op[k].x - on[k].x), coef * (op[k].y - on[k].y),
+                              coef * (op[k].z - on[k].z), coef * (op[k].w - on[k].w));
+      float4 gp = make_float4(coef * ou[k].x, coef * ou[k].y, coef * ou[k].z, coef * ou[k].w);
+      float4 gn = make_float4(-gp.x, -gp.y, -gp.z, -gp.w);
+      atomicAdd(reinterpret_cast<float4*>(grad_out + (size_t)u * ld + 4 * c), gu);
+      atomicAdd(reinterpret_cast<float4*>(grad_out + (size_t)p * ld + 4 * c), gp);
+      atomicAdd(reinterpret_cast<float4*>(grad_out + (size_t)n * ld + 4 * c), gn);
+      if (grad_e0) {
+        float4 a = ldg_f4(e0 + (size_t)u * ld + 4 * c), b = ldg_f4(e0 + (size_t)p * ld + 4 * c),
+               d = ldg_f4(e0 + (size_t)n * ld + 4 * c);
+        const float r = decay_over_batch;
+        float4 zu = make_float4(fmaf(alpha0, gu.x, r * a.x), fmaf(alpha0, gu.y, r * a.y),
+                                fmaf(alpha0, gu.z, r * a.z), fmaf(alpha0, gu.w, r * a.w));
+        float4 zp = make_float4(fmaf(alpha0, gp.x, r * b.x), fmaf(alpha0, gp.y, r * b.y),
+                                fmaf(alpha0, gp.z, r * b.z), fmaf(alpha0, gp.w, r * b.w));
+        float4 zn = make_float4(fmaf(alpha0, gn.x, r * d.x), fmaf(alpha0, gn.y, r * d.y),
+                                fmaf(alpha0, gn.z, r * d.z), fmaf(alpha0, gn.w, r * d.w));
+        atomicAdd(reinterpret_cast<float4*>(grad_e0 + (size_t)u * ld + 4 * c), zu);
+        atomicAdd(reinterpret_cast<float4*>(grad_e0 + (size_t)p * ld + 4 * c), zp);
+        atomicAdd(reinterpret_cast<float4*>(grad_e0 + (size_t)n * ld + 4 * c), zn);
+      }
+    }
+  }
+}
+
+// Deterministic reduction of the per-triple terms (fixed tree, double accumulators).
+__global__ void k_bpr_reduce(const float* __restrict__ per_triple, int64_t batch, double decay,
+                             float* __restrict__ loss3) {
+  __shared__ double s_loss[256], s_sq[256];
+  double a = 0.0, b = 0.0;
+  for (int64_t t = threadIdx.x; t < batch; t += 256) { a += per_triple[2 * t]; b += per_triple[2 * t + 1]; }
+  s_loss[threadIdx.x] = a; s_sq[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { s_loss[threadIdx.x] += s_loss[threadIdx.x + o]; s_sq[threadIdx.x] += s_sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float bpr = (float)(s_loss[0] / (double)batch);
+    float reg = (float)(0.5 * s_sq[0] / (double)batch * decay);
+    loss3[0] = bpr; loss3[1] = reg; loss3[2] = bpr + reg;
+  }
+}
+
+__global__ void k_adam(int64_t n4, float4* __restrict__ p, const float4* __restrict__ g,
+                       float4* __restrict__ m, float4* __restrict__ v, AdamScalars s) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = __ldcs(g + i), mm = __ldcs(m + i), vv = __ldcs(v + i);
+    adam_update(pp.x, mm.x, vv.x, gg.x, s);
+    adam_update(pp.y, mm.y, vv.y, gg.y, s);
+    adam_update(pp.z, mm.z, vv.z, gg.z, s);
+    adam_update(pp.w, mm.w, vv.w, gg.w, s);
+    p[i] = pp; __stcs(m + i, mm); __stcs(v + i, vv);
+  }
+}
+
+__global__ void k_adam_tail(int64_t beg, int64_t n, float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, AdamScalars s) {
+  int64_t i = beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) adam_update(p[i], m[i], v[i], g[i], s);
+}
+
+}  // namespace
+
+int bpr_launch(int64_t num_nodes, int ld, int64_t batch, const int64_t* users, const int64_t* pos,
+               const int64_t* neg, const float* out, const float* e0, double decay, float alpha0,
+               float* grad_out, float* grad_e0, int32_t* touched, float* loss3, float* per_triple,
+               int* bad, cudaStream_t st) {
+  const int threads = 256;
+  const int grid = (int)ceil_div(batch * 32, threads);
+  k_bpr<<<grid, threads, 0, st>>>(num_nodes, ld, batch, users, pos, neg, out, e0,
+                                  (float)(1.0 / (double)batch), (float)(decay / (double)batch), alpha0,
+                                  grad_out, grad_e0, touched, per_triple, bad);
+  LGC_LAUNCH_CHECK();
+  k_bpr_reduce<<<1, 256, 0, st>>>(per_triple, batch, decay, loss3);
+  LGC_LAUNCH_CHECK();
+  return LGC_OK;
+}
+
+}  // namespace lgc
+
+using namespace lgc;
+
+extern "C" int lgc_pair_scores(int ld, const float* out, const int64_t* pairs, int64_t n_pairs,
+                               float* score, void* stream) {
+  LGC_REQUIRE(out && pairs && score, "null argument");
+  LGC_REQUIRE(ld > 0 && ld % 4 == 0, "ld must be a positive multiple of 4");
+  if (n_pairs == 0) return LGC_OK;
+  k_pair_scores<<<(int)ceil_div(n_pairs * 32, 256), 256, 0, (cudaStream_t)stream>>>(out, ld, pairs,
+                                                                                     n_pairs, score);
+  LGC_LAUNCH_CHECK();
+  return LGC_OK;
+}
+
+extern "C" size_t lgc_bpr_workspace_bytes(int64_t batch) {
+  return (size_t)batch * 2 * sizeof(float) + 16;
+}
+
+extern "C" int lgc_bpr_loss_grad(int64_t num_nodes, int ld, int64_t batch, const int64_t* users,
+                                 const int64_t* pos, const int64_t* neg, const float* out,
+                                 const float* e0, double decay, float alpha0, float* grad_out,
+                                 float* grad_e0, int32_t* touched, float* loss3, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  LGC_REQUIRE(users && pos && neg && out && e0 && grad_out && loss3 && workspace, "null argument");
+  LGC_REQUIRE(batch > 0, "batch must be positive");
+  LGC_REQUIRE(ld > 0 && ld % 4 == 0 && ld <= 128 * kMaxVecPerLane, "unsupported ld");
+  if (workspace_bytes < lgc_bpr_workspace_bytes(batch)) {
+    set_error("lgc_bpr_loss_grad: workspace too small");
+    return LGC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int* bad = (int*)workspace;
+  float* per_triple = (float*)((char*)workspace + 16);
+  LGC_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  int rc = bpr_launch(num_nodes, ld, batch, users, pos, neg, out, e0, decay, alpha0, grad_out, grad_e0,
+                      touched, loss3, per_triple, bad, st);
+  return rc;
+}
+
+extern "C" int lgc_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr,
+                             double beta1, double beta2, double eps, int64_t step, void* stream) {
+  LGC_REQUIRE(p && g && m && v, "null argument");
+  LGC_REQUIRE(n >= 0 && step >= 1, "bad size or step");
+  LGC_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0,
+              "buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamScalars s = make_adam_scalars(lr, beta1, beta2, eps, step);
+  const int64_t n4 = n / 4;
+  if (n4) {
+    int grid = (int)std::min<int64_t>(ceil_div(n4, 256), kNumSMs * 16);
+    k_adam<<<grid, 256, 0, st>>>(n4, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, s);
+    LGC_LAUNCH_CHECK();
+  }
+  if (n % 4) {
+    k_adam_tail<<<1, 32, 0, st>>>(n4 * 4, n, p, g, m, v, s);
+    LGC_LAUNCH_CHECK();
+  }
+  return LGC_OK;
+}

@@ -1,0 +1,99 @@
+// Shared helpers for liblgc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "lgc_b200.h"
+
+namespace lgc {
+
+void set_error(const std::string& msg);
+
+#define LGC_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::lgc::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                       __FILE__ + ":" + std::to_string(__LINE__) + ")");                 \
+      return LGC_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define LGC_REQUIRE(cond, msg)                                                           \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ::lgc::set_error(std::string(msg) + " [" #cond "]");                               \
+      return LGC_ERR_INVALID;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define LGC_LAUNCH_CHECK() LGC_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;  // B200
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float4 ld_f4(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+// streaming store: written once, not re-read by this kernel
+__device__ __forceinline__ void st_f4_cs(float* p, float4 v) {
+  __stcs(reinterpret_cast<float4*>(p), v);
+}
+__device__ __forceinline__ float4 ld_f4_cs(const float* p) {
+  return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 fma4(float w, float4 x, float4 a) {
+  a.x = fmaf(w, x.x, a.x);
+  a.y = fmaf(w, x.y, a.y);
+  a.z = fmaf(w, x.z, a.z);
+  a.w = fmaf(w, x.w, a.w);
+  return a;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// ---- table-row geometry: a row of `ld` floats = VEC float4 = L lanes x V float4 per lane.
+struct RowShape {
+  int L, V;
+};
+static inline bool row_shape(int ld, RowShape* rs) {
+  if (ld <= 0 || ld % 4) return false;
+  int vec = ld / 4, L = 16;
+  while (L > 1 && vec % L) L >>= 1;
+  int V = vec / L;
+  if (V > 5) return false;
+  rs->L = L;
+  rs->V = V;
+  return true;
+}
+
+}  // namespace lgc
+
+// Opaque graph handle (definition shared by the .cu files).
+struct lgc_graph {
+  int64_t num_nodes = 0, nnz = 0;
+  int is_symmetric = 0;
+  int light_max_degree = 0;
+  int64_t num_heavy_rows = 0, num_chunks = 0, num_split_rows = 0;
+  int32_t* rowptr = nullptr;
+  int32_t* src = nullptr;
+  int32_t* eid = nullptr;
+  float* w_hat = nullptr;
+  float* deg = nullptr;
+  float* dis = nullptr;
+  // heavy-row schedule
+  int4* chunks = nullptr;       // {row, beg, end, partial_slot or -1}
+  int4* split_rows = nullptr;   // {row, first_slot, n_slots, 0}
+  int64_t num_partial_slots = 0;   // one [ld] partial row per chunk of a split row (workspace)
+};

@@ -1,0 +1,352 @@
+// CSR SpMM  Y = A_hat X  with fused epilogues -- the LGConv hot kernel
+// (replaces PyG gather + mul + scatter_add, K2-K5 of SURVEY.md 2.3; call site src/lightgcn.py:96).
+//
+// HBM-bound gather/accumulate. A table row of `ld` floats is VEC = ld/4 float4 = L lanes x V
+// float4 per lane, so every gather of a neighbour row is a run of 128-bit loads that covers whole
+// 32-byte sectors. Three launches per layer, all deterministic (no atomics):
+//   light : rows with in-degree <= 32, natural row order, one L-lane sub-warp per row
+//           (the power-law tail: ~97 % of the user rows), streaming writes stay sequential;
+//   heavy : rows above that are pre-cut (graph build) into work items of <= 256 edges, one warp
+//           each, 32/L edge streams per warp; rows that fit one item finish in place, split rows
+//           write a partial row;
+//   finish: split rows add their partials in order and apply the epilogue.
+// The epilogue fuses what the reference runs as separate ATen passes: the running layer mean
+// `out = out + x * alpha` (src/lightgcn.py:93,97), the backward Horner add, and dense Adam.
+#include "spmm.cuh"
+
+namespace lgc {
+namespace {
+
+template <int MODE>
+__device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s) {
+  if (MODE == EPI_PLAIN) {
+    float4 r = make_float4(a.scale * s.x, a.scale * s.y, a.scale * s.z, a.scale * s.w);
+    if (a.addend) {
+      float4 g = ldg_f4(a.addend + off);
+      r.x = fmaf(a.beta, g.x, r.x); r.y = fmaf(a.beta, g.y, r.y);
+      r.z = fmaf(a.beta, g.z, r.z); r.w = fmaf(a.beta, g.w, r.w);
+    }
+    st_f4(a.y + off, r);
+  } else if (MODE == EPI_FWD_INIT) {
+    if (a.y) st_f4(a.y + off, s);
+    float4 x = ldg_f4(a.xrow + off), r;   // out = x * alpha0; out = out + x1 * alpha1
+    r.x = __fadd_rn(__fmul_rn(x.x, a.a0), __fmul_rn(s.x, a.a1));
+    r.y = __fadd_rn(__fmul_rn(x.y, a.a0), __fmul_rn(s.y, a.a1));
+    r.z = __fadd_rn(__fmul_rn(x.z, a.a0), __fmul_rn(s.z, a.a1));
+    r.w = __fadd_rn(__fmul_rn(x.w, a.a0), __fmul_rn(s.w, a.a1));
+    st_f4_cs(a.acc + off, r);
+  } else if (MODE == EPI_FWD_RMW) {
+    if (a.y) st_f4(a.y + off, s);
+    float4 o = ld_f4_cs(a.acc + off);
+    o.x = __fadd_rn(o.x, __fmul_rn(s.x, a.a1)); o.y = __fadd_rn(o.y, __fmul_rn(s.y, a.a1));
+    o.z = __fadd_rn(o.z, __fmul_rn(s.z, a.a1)); o.w = __fadd_rn(o.w, __fmul_rn(s.w, a.a1));
+    st_f4_cs(a.acc + off, o);
+  } else {  // EPI_ADAM
+    float4 z = ld_f4_cs(a.addend + off);
+    float4 p = ld_f4(a.p + off), m = ld_f4_cs(a.m + off), v = ld_f4_cs(a.v + off);
+    adam_update(p.x, m.x, v.x, fmaf(a.scale, s.x, z.x), a.adam);
+    adam_update(p.y, m.y, v.y, fmaf(a.scale, s.y, z.y), a.adam);
+    adam_update(p.z, m.z, v.z, fmaf(a.scale, s.z, z.z), a.adam);
+    adam_update(p.w, m.w, v.w, fmaf(a.scale, s.w, z.w), a.adam);
+    st_f4(a.p + off, p);
+    st_f4_cs(a.m + off, m);
+    st_f4_cs(a.v + off, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------- light rows
+template <int L, int V, int MODE>
+__global__ void __launch_bounds__(256) k_spmm_light(const int32_t* __restrict__ rowptr,
+                                                    const int32_t* __restrict__ src,
+                                                    const float* __restrict__ w,
+                                                    const float* __restrict__ x, int num_rows,
+                                                    int light_max, EpiArgs args) {
+  constexpr int RPW = 32 / L;        // rows per warp
+  constexpr int LD = 4 * L * V;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L;
+  const unsigned sub_mask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t row = warp * RPW + sub;
+  if (row >= num_rows) return;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  if (end - beg > light_max) return;  // heavy path owns this row
+
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = beg; base < end; base += L) {
+    // one coalesced load brings up to L (source, weight) pairs of this row
+    int my_s = 0; float my_w = 0.f;
+    if (base + sl < end) { my_s = src[base + sl]; my_w = w[base + sl]; }
+    const int n = min(L, end - base);
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      int s[4]; float ww[4]; float4 xv[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] = __shfl_sync(sub_mask, my_s, sub * L + ((j0 + u) & (L - 1)));
+        ww[u] = __shfl_sync(sub_mask, my_w, sub * L + ((j0 + u) & (L - 1)));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < n) {
+          const float* xr = x + (size_t)s[u] * LD + 4 * sl;
+#pragma unroll
+          for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < n) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = fma4(ww[u], xv[u][v], acc[v]);
+        }
+    }
+  }
+  const size_t off = (size_t)row * LD + 4 * sl;
+#pragma unroll
+  for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+}
+
+// ---------------------------------------------------------------------------------- heavy rows
+template <int L, int V, int MODE>
+__global__ void __launch_bounds__(256) k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks,
+                                                    const int32_t* __restrict__ src,
+                                                    const float* __restrict__ w,
+                                                    const float* __restrict__ x,
+                                                    float* __restrict__ partials, EpiArgs args) {
+  constexpr int RPW = 32 / L;        // edge streams per warp
+  constexpr int LD = 4 * L * V;
+  constexpr int U = (L >= 8) ? 8 : L;  // gathers in flight per stream and unrolled step
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (warp >= num_chunks) return;
+  const int4 c = chunks[warp];
+  const int row = c.x, beg = c.y, end = c.z, slot = c.w;
+
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = beg; base < end; base += 32) {
+    int my_s = 0; float my_w = 0.f;
+    if (base + lane < end) { my_s = src[base + lane]; my_w = w[base + lane]; }
+    const int n = min(32, end - base);
+    // stream `sub` takes entries sub, sub+RPW, ... of this block of 32
+#pragma unroll
+    for (int t0 = 0; t0 < L; t0 += U) {
+      int s[U]; float ww[U]; float4 xv[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = (t0 + u) * RPW + sub;
+        s[u] = __shfl_sync(0xffffffffu, my_s, idx);
+        ww[u] = __shfl_sync(0xffffffffu, my_w, idx);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if ((t0 + u) * RPW + sub < n) {
+          const float* xr = x + (size_t)s[u] * LD + 4 * sl;
+#pragma unroll
+          for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if ((t0 + u) * RPW + sub < n) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = fma4(ww[u], xv[u][v], acc[v]);
+        }
+    }
+  }
+  // combine the RPW edge streams (fixed order: deterministic)
+#pragma unroll
+  for (int o = L; o < 32; o <<= 1) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+      acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+      acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+      acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+    }
+  }
+  if (sub != 0) return;
+  if (slot >= 0) {
+    float* pr = partials + (size_t)slot * LD + 4 * sl;
+#pragma unroll
+    for (int v = 0; v < V; ++v) st_f4(pr + 4 * L * v, acc[v]);
+  } else {
+    const size_t off = (size_t)row * LD + 4 * sl;
+#pragma unroll
+    for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+  }
+}
+
+template <int L, int V, int MODE>
+__global__ void __launch_bounds__(256) k_spmm_finish(const int4* __restrict__ split_rows, int num_split,
+                                                     const float* __restrict__ partials, EpiArgs args) {
+  constexpr int RPW = 32 / L;
+  constexpr int LD = 4 * L * V;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t i = warp * RPW + sub;
+  if (i >= num_split) return;
+  const int4 r = split_rows[i];
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < r.z; ++k) {
+    const float* pr = partials + (size_t)(r.y + k) * LD + 4 * sl;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], ld_f4(pr + 4 * L * v));
+  }
+  const size_t off = (size_t)r.x * LD + 4 * sl;
+#pragma unroll
+  for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+}
+
+template <int L, int V, int MODE>
+int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
+  constexpr int RPW = 32 / L;
+  const int threads = 256, wpb = threads / 32;
+  const int64_t n = g->num_nodes;
+  const int grid_light = (int)ceil_div(ceil_div(n, RPW), wpb);
+  k_spmm_light<L, V, MODE><<<grid_light, threads, 0, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
+                                                            g->light_max_degree, a);
+  LGC_LAUNCH_CHECK();
+  if (g->num_chunks > 0) {
+    const int grid_heavy = (int)ceil_div(g->num_chunks, wpb);
+    k_spmm_heavy<L, V, MODE><<<grid_heavy, threads, 0, st>>>(g->chunks, (int)g->num_chunks, g->src,
+                                                              g->w_hat, x, partials, a);
+    LGC_LAUNCH_CHECK();
+  }
+  if (g->num_split_rows > 0) {
+    const int grid_fin = (int)ceil_div(ceil_div(g->num_split_rows, RPW), wpb);
+    k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, st>>>(g->split_rows, (int)g->num_split_rows,
+                                                             partials, a);
+    LGC_LAUNCH_CHECK();
+  }
+  return LGC_OK;
+}
+
+template <int L, int V>
+int launch_mode(const lgc_graph* g, const float* x, EpiMode mode, const EpiArgs& a, float* partials,
+                cudaStream_t st) {
+  switch (mode) {
+    case EPI_PLAIN: return launch_lv<L, V, EPI_PLAIN>(g, x, a, partials, st);
+    case EPI_FWD_INIT: return launch_lv<L, V, EPI_FWD_INIT>(g, x, a, partials, st);
+    case EPI_FWD_RMW: return launch_lv<L, V, EPI_FWD_RMW>(g, x, a, partials, st);
+    case EPI_ADAM: return launch_lv<L, V, EPI_ADAM>(g, x, a, partials, st);
+  }
+  return LGC_ERR_INVALID;
+}
+
+__global__ void k_scale(const float4* __restrict__ x, float4* __restrict__ y, float a, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    y[i] = make_float4(v.x * a, v.y * a, v.z * a, v.w * a);
+  }
+}
+
+}  // namespace
+
+size_t spmm_partials_floats(const lgc_graph* g, int ld) {
+  return (size_t)g->num_partial_slots * (size_t)ld;
+}
+
+int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const EpiArgs& a,
+                float* partials, cudaStream_t st) {
+  RowShape rs;
+  if (!row_shape(ld, &rs)) {
+    set_error("unsupported row width ld=" + std::to_string(ld));
+    return LGC_ERR_UNSUPPORTED;
+  }
+#define LGC_CASE(LL, VV) \
+  if (rs.L == LL && rs.V == VV) return launch_mode<LL, VV>(g, x, mode, a, partials, st);
+  LGC_CASE(16, 1) LGC_CASE(16, 2) LGC_CASE(16, 3) LGC_CASE(16, 4)
+  LGC_CASE(8, 1) LGC_CASE(8, 3) LGC_CASE(8, 5)
+  LGC_CASE(4, 1) LGC_CASE(4, 3) LGC_CASE(4, 5)
+  LGC_CASE(2, 1) LGC_CASE(1, 1)
+#undef LGC_CASE
+  set_error("no kernel instantiation for ld=" + std::to_string(ld));
+  return LGC_ERR_UNSUPPORTED;
+}
+
+}  // namespace lgc
+
+using namespace lgc;
+
+extern "C" int lgc_ld_supported(int ld) {
+  RowShape rs;
+  if (!row_shape(ld, &rs)) return 0;
+  const int ok[][2] = {{16, 1}, {16, 2}, {16, 3}, {16, 4}, {8, 1}, {8, 3}, {8, 5},
+                       {4, 1},  {4, 3},  {4, 5},  {2, 1},  {1, 1}};
+  for (auto& p : ok)
+    if (p[0] == rs.L && p[1] == rs.V) return 1;
+  return 0;
+}
+
+extern "C" size_t lgc_spmm_workspace_bytes(const lgc_graph_t* g, int ld) {
+  return g ? spmm_partials_floats(g, ld) * sizeof(float) : 0;
+}
+
+extern "C" int lgc_spmm(const lgc_graph_t* g, int ld, const float* x, float* y, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  LGC_REQUIRE(g && x && y, "null argument");
+  LGC_REQUIRE(x != y, "x and y must not alias");
+  if (workspace_bytes < lgc_spmm_workspace_bytes(g, ld)) {
+    set_error("lgc_spmm: workspace too small");
+    return LGC_ERR_WORKSPACE;
+  }
+  EpiArgs a;
+  a.y = y;
+  return launch_spmm(g, ld, x, EPI_PLAIN, a, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" size_t lgc_propagate_workspace_bytes(const lgc_graph_t* g, int ld, int num_layers) {
+  if (!g) return 0;
+  size_t t = (size_t)g->num_nodes * ld;
+  size_t n_tmp = num_layers > 2 ? 2 : (num_layers > 1 ? 1 : 0);
+  return (n_tmp * t + spmm_partials_floats(g, ld)) * sizeof(float);
+}
+
+extern "C" int lgc_propagate(const lgc_graph_t* g, int ld, int num_layers, const float* h_alpha,
+                             const float* x0, float* out, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  LGC_REQUIRE(g && h_alpha && x0 && out, "null argument");
+  LGC_REQUIRE(num_layers >= 0, "num_layers < 0");
+  LGC_REQUIRE(x0 != out, "x0 and out must not alias");
+  if (workspace_bytes < lgc_propagate_workspace_bytes(g, ld, num_layers)) {
+    set_error("lgc_propagate: workspace too small");
+    return LGC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t t = (size_t)g->num_nodes * ld;
+  if (num_layers == 0) {
+    k_scale<<<kNumSMs * 8, 256, 0, st>>>((const float4*)x0, (float4*)out, h_alpha[0], (int64_t)(t / 4));
+    LGC_LAUNCH_CHECK();
+    return LGC_OK;
+  }
+  float* ws = (float*)workspace;
+  float* tmp[2] = {ws, ws + t};
+  float* partials = ws + (num_layers > 2 ? 2 : (num_layers > 1 ? 1 : 0)) * t;
+  const float* cur = x0;
+  for (int l = 1; l <= num_layers; ++l) {
+    EpiArgs a;
+    a.acc = out;
+    a.a1 = h_alpha[l];
+    a.y = (l < num_layers) ? tmp[(l - 1) & 1] : nullptr;   // the last layer's x is never read
+    int rc;
+    if (l == 1) {
+      a.a0 = h_alpha[0];
+      a.xrow = x0;
+      rc = launch_spmm(g, ld, cur, EPI_FWD_INIT, a, partials, st);
+    } else {
+      rc = launch_spmm(g, ld, cur, EPI_FWD_RMW, a, partials, st);
+    }
+    if (rc) return rc;
+    cur = a.y;
+  }
+  return LGC_OK;
+}

@@ -1,0 +1,63 @@
+// Internal interface of the CSR SpMM (shared by spmm.cu and train_step.cu).
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace lgc {
+
+enum EpiMode : int {
+  EPI_PLAIN = 0,     // y = scale * (A x)[r] + beta * addend[r]          (LGConv; backward Horner)
+  EPI_FWD_INIT = 1,  // acc = a0 * x[r] + a1 * (A x)[r];  y = (A x)[r] if y != null
+  EPI_FWD_RMW = 2,   // acc += a1 * (A x)[r];             y = (A x)[r] if y != null
+  EPI_ADAM = 3       // g = scale * (A x)[r] + addend[r]; Adam update of p, m, v at row r
+};
+
+struct AdamScalars {
+  float one_minus_beta1, beta2, one_minus_beta2, bc2_sqrt, eps, neg_step_size;
+};
+
+struct EpiArgs {
+  float* y = nullptr;
+  float* acc = nullptr;
+  const float* xrow = nullptr;
+  const float* addend = nullptr;
+  float a0 = 0.f, a1 = 0.f, scale = 1.f, beta = 0.f;
+  float* p = nullptr;
+  float* m = nullptr;
+  float* v = nullptr;
+  AdamScalars adam = {};
+};
+
+// torch.optim.Adam (single-tensor path, no amsgrad / weight decay) on one element, with the
+// operation order of ATen's CPU kernels (lerp_, mul_+addcmul_, sqrt/div/add_, addcdiv_).
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g,
+                                            const AdamScalars& s) {
+  m = fmaf(s.one_minus_beta1, __fsub_rn(g, m), m);
+  v = __fadd_rn(__fmul_rn(v, s.beta2), __fmul_rn(__fmul_rn(s.one_minus_beta2, g), g));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
+  p = __fadd_rn(p, __fdiv_rn(__fmul_rn(s.neg_step_size, m), denom));
+}
+
+static inline AdamScalars make_adam_scalars(double lr, double beta1, double beta2, double eps,
+                                            int64_t step) {
+  double bc1 = 1.0 - pow(beta1, (double)step);
+  double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars s;
+  s.one_minus_beta1 = (float)(1.0 - beta1);
+  s.beta2 = (float)beta2;
+  s.one_minus_beta2 = (float)(1.0 - beta2);
+  s.bc2_sqrt = (float)sqrt(bc2);
+  s.eps = (float)eps;
+  s.neg_step_size = (float)(-(lr / bc1));
+  return s;
+}
+
+// floats of scratch the heavy-row two-phase reduce needs for this graph and row width
+size_t spmm_partials_floats(const lgc_graph* g, int ld);
+
+// y/acc/... = epilogue(A_hat x). `partials` must hold spmm_partials_floats() floats.
+int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const EpiArgs& args,
+                float* partials, cudaStream_t stream);
+
+}  // namespace lgc

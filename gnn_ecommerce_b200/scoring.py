@@ -1,0 +1,95 @@
+"""Top-k scoring wrapper (`recommendK`, reference `src/lightgcn.py:169-182`).
+
+Host side only converts the reference's dense seen-mask into CSR seen-lists and hands raw
+pointers to `lgc_score_topk`; the GEMM, the candidate filter, the exact fp32 re-scoring and the
+multiplicative mask all run in `csrc/score.cu`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _capi
+from .graph import _ptr, _stream
+
+
+@dataclass
+class SeenLists:
+    """CSR of already-seen (train purchase) items per scored user: row i belongs to
+    `user_id_list[i]`. Sparse form of `interactions_t` (reference `src/utils_v2.py:92-103,137`)."""
+    ptr: Optional[Tensor]      # int64 [U+1] on the device, or None (nothing seen)
+    items: Optional[Tensor]    # int64, un-offset item ids
+
+    @staticmethod
+    def from_numpy(ptr: np.ndarray, items: np.ndarray, device) -> "SeenLists":
+        return SeenLists(torch.as_tensor(np.asarray(ptr, dtype=np.int64), device=device),
+                         torch.as_tensor(np.asarray(items, dtype=np.int64), device=device))
+
+
+def as_seen_lists(interactions_t, n_rows: int, n_items: int, device) -> SeenLists:
+    if interactions_t is None:
+        return SeenLists(None, None)
+    if isinstance(interactions_t, SeenLists):
+        return interactions_t
+    t = interactions_t
+    if t.is_sparse:
+        t = t.coalesce()
+        idx, val = t.indices(), t.values()
+        if not bool(((val == 0) | (val == 1)).all()):
+            raise NotImplementedError("recommendK: the seen-mask must be 0/1")
+        keep = val != 0
+        rows, cols = idx[0][keep], idx[1][keep]
+    else:
+        if tuple(t.shape) != (n_rows, n_items):
+            raise ValueError(f"interactions_t must be [{n_rows}, {n_items}], got {tuple(t.shape)}")
+        if not bool(((t == 0) | (t == 1)).all()):
+            raise NotImplementedError("recommendK: the seen-mask must be 0/1")
+        nz = t.nonzero()
+        rows, cols = nz[:, 0], nz[:, 1]            # row-major order: rows ascend
+    counts = torch.bincount(rows, minlength=n_rows)
+    ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=rows.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    order = torch.argsort(rows, stable=True)
+    return SeenLists(ptr.to(device), cols[order].to(device=device, dtype=torch.int64).contiguous())
+
+
+def score_topk(user_emb: Tensor, item_emb: Tensor, user_ids: Optional[Tensor],
+               seen_ptr: Optional[Tensor], seen_items: Optional[Tensor], k: int,
+               d: Optional[int] = None, return_stats: bool = False):
+    """Top-k items per user by masked fp32 score. `user_emb` / `item_emb` are row tables
+    (row stride = `stride(0)` floats, multiple of 4); `d` = number of leading columns used."""
+    lib = _capi.lib()
+    for t, name in ((user_emb, "user_emb"), (item_emb, "item_emb")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+            raise ValueError(f"{name} must be a 2-D float32 CUDA row table (no CPU fallback)")
+    d = int(d if d is not None else min(user_emb.size(1), item_emb.size(1)))
+    n_items = item_emb.size(0)
+    if user_ids is None:
+        n_users = user_emb.size(0)
+    else:
+        user_ids = user_ids.to(device=user_emb.device, dtype=torch.int64).contiguous()
+        n_users = user_ids.numel()
+    if not 1 <= k <= min(32, n_items):
+        raise ValueError("k must be in 1..min(32, n_items)")
+    dev = user_emb.device
+    items = torch.empty(n_users, k, dtype=torch.int64, device=dev)
+    scores = torch.empty(n_users, k, dtype=torch.float32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    if n_users == 0:
+        return (items, scores, stats) if return_stats else (items, scores)
+    ws = torch.empty(lib.lgc_score_topk_workspace_bytes(n_users, n_items, d, k), dtype=torch.uint8,
+                     device=dev)
+    args = _capi.ScoreTopkArgs(
+        d=d, ld_user=user_emb.stride(0), ld_item=item_emb.stride(0), k=k, n_users=n_users,
+        n_items=n_items, user_emb=_ptr(user_emb), item_emb=_ptr(item_emb), user_ids=_ptr(user_ids),
+        seen_ptr=_ptr(seen_ptr), seen_items=_ptr(seen_items), topk_items=_ptr(items),
+        topk_scores=_ptr(scores), stats=_ptr(stats), workspace=_ptr(ws), workspace_bytes=ws.numel())
+    with torch.cuda.device(dev):
+        rc = lib.lgc_score_topk(C.byref(args), _stream())
+    _capi.check(rc, "lgc_score_topk")
+    return (items, scores, stats) if return_stats else (items, scores)

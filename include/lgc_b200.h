@@ -1,0 +1,203 @@
+/*
+ * lgc_b200.h -- C ABI of the B200-native LightGCN hot path (liblgc_b200.so).
+ *
+ * The reference (happykygo/GNN-eCommerce) has no FFI of its own: its boundary for this path is
+ * the Python operator call `LGConv.forward(x, edge_index, edge_weight)` (src/lightgcn.py:96)
+ * inside the `LightGCN` module (src/lightgcn.py:13-231), driven by
+ * `TrainLightGCN.mini_batch_loop` (src/train_lightgcn.py:123-153) and `LightGCN.recommendK`
+ * (src/lightgcn.py:169-182). Each entry point below names the reference lines it replaces.
+ * The binding a maintainer adds on the reference side is the ctypes stub shown in
+ * INTEGRATION.md (shipped as gnn_ecommerce_b200/_capi.py).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes; every pointer is a DEVICE pointer unless its name starts
+ *     with `h_`; no torch types, no C++ exceptions cross this boundary;
+ *   - every call takes an explicit `cudaStream_t` (passed as void*) and is asynchronous on it
+ *     unless stated otherwise; no call allocates device memory except `lgc_graph_build*`
+ *     (owned by the handle) -- workspaces are sized by `*_workspace_bytes` and passed in;
+ *   - return value: 0 on success, negative `lgc_status` on failure; `lgc_last_error()` returns
+ *     a thread-local message;
+ *   - embedding tables are row-major fp32 `[num_nodes, ld]` with `ld % 4 == 0`, `ld >= d`,
+ *     16-byte aligned base, padding columns (d..ld-1) zero. Node ids follow the reference:
+ *     users 0..n_users-1, items n_users..N-1 (src/utils_v2.py:128).
+ */
+#ifndef LGC_B200_H
+#define LGC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGC_ABI_VERSION 1
+
+typedef enum {
+  LGC_OK = 0,
+  LGC_ERR_INVALID = -1,      /* bad argument (null pointer, size, unsupported ld)           */
+  LGC_ERR_CUDA = -2,         /* a CUDA runtime call or kernel launch failed                  */
+  LGC_ERR_INDEX_RANGE = -3,  /* a node id is outside [0, num_nodes) (reference: device assert) */
+  LGC_ERR_WORKSPACE = -4,    /* workspace too small                                          */
+  LGC_ERR_UNSUPPORTED = -5
+} lgc_status;
+
+typedef struct lgc_graph lgc_graph_t; /* opaque, owns its device arrays */
+
+int lgc_abi_version(void);
+const char* lgc_last_error(void);
+/* 1 if `ld` (floats per table row) has a kernel instantiation, else 0. */
+int lgc_ld_supported(int ld);
+
+/* ------------------------------------------------------------------ graph build (once per graph)
+ * Replaces what PyG `gcn_norm` recomputes inside EVERY LGConv.forward call (K times per step;
+ * call site src/lightgcn.py:96) on the edge list produced by `df_to_graph`
+ * (src/utils_v2.py:146-165):
+ *   deg[v]  = sum of w_e over edges whose target is v, accumulated in edge-list order (bit-exact
+ *             to the CPU `scatter_add_`), dis = deg^-1/2 with inf -> 0,
+ *   w_hat_e = (dis[src_e] * w_e) * dis[dst_e],
+ * and a destination-major CSR (stable: edges of a row keep their list order).
+ * `d_edge_index` is int64 [2, nnz] row-major (row 0 = source, row 1 = target);
+ * `d_edge_weight` may be NULL (all ones). `normalize == 0` uses the weights as given
+ * (already-normalised operator, e.g. the transpose of a non-symmetric graph).
+ * Synchronises `stream` before returning (it reads back a few counters). */
+int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* d_edge_index,
+                    const float* d_edge_weight, int normalize, void* stream,
+                    lgc_graph_t** out_graph);
+int lgc_graph_destroy(lgc_graph_t* graph);
+
+typedef struct {
+  int64_t num_nodes;
+  int64_t nnz;
+  int32_t is_symmetric;      /* A_hat == A_hat^T (both directions, equal weights): backward may
+                                reuse the forward operator                                     */
+  int32_t light_max_degree;  /* rows up to this in-degree take the sub-warp path               */
+  int64_t num_heavy_rows;    /* rows above it                                                  */
+  int64_t num_chunks;        /* warp-sized work items the heavy rows were cut into             */
+  int64_t num_split_rows;    /* heavy rows spanning more than one chunk (two-phase reduce)     */
+  /* device arrays owned by the handle (valid until destroy) */
+  const int32_t* rowptr;     /* [num_nodes+1]                                                  */
+  const int32_t* src;        /* [nnz] source node of every CSR entry                           */
+  const int32_t* eid;        /* [nnz] position of the entry in the input edge list             */
+  const float* w_hat;        /* [nnz] normalised weight, CSR order                             */
+  const float* deg;          /* [num_nodes] fp32 weighted in-degree                            */
+  const float* dis;          /* [num_nodes] deg^-1/2, 0 for isolated nodes                     */
+} lgc_graph_info;
+int lgc_graph_get_info(const lgc_graph_t* graph, lgc_graph_info* info);
+
+/* ------------------------------------------------------------------ LGConv (src/lightgcn.py:96)
+ * y = A_hat x. x, y: [num_nodes, ld]; must not alias. Workspace holds the partial rows of the
+ * hub rows that are split over several warps (usually a few MB; may be 0 bytes). */
+size_t lgc_spmm_workspace_bytes(const lgc_graph_t* graph, int ld);
+int lgc_spmm(const lgc_graph_t* graph, int ld, const float* x, float* y, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ get_embedding (src/lightgcn.py:91-99)
+ * out = sum_{l=0..K} alpha_l A_hat^l x0, evaluated like the reference as a running sum but
+ * fused into the SpMM epilogue. `h_alpha` is a HOST array of K+1 floats. Because A_hat is
+ * symmetric for the reference's graphs the same call is the backward pass (x0 := dL/dout).
+ * Workspace: lgc_propagate_workspace_bytes(). out must not alias x0. */
+size_t lgc_propagate_workspace_bytes(const lgc_graph_t* graph, int ld, int num_layers);
+int lgc_propagate(const lgc_graph_t* graph, int ld, int num_layers, const float* h_alpha,
+                  const float* x0, float* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------ pair scores (src/lightgcn.py:123-125)
+ * score[j] = <out[src_j], out[dst_j]>, j < n_pairs; `pairs` is int64 [2, n_pairs]. */
+int lgc_pair_scores(int ld, const float* out, const int64_t* pairs, int64_t n_pairs, float* score,
+                    void* stream);
+
+/* ------------------------------------------------------------------ BPR loss + gradients
+ * Replaces, for pre-sampled triples (users, pos, neg: int64 [batch]):
+ *   forward gathers + dot (src/lightgcn.py:123-125), mean softplus(-(s+ - s-))
+ *   (src/lightgcn.py:279-286, src/train_lightgcn.py:141), the layer-0 L2 term
+ *   (src/utils_v2.py:193-211) and their backward (src/train_lightgcn.py:146).
+ * loss3 <- {bpr, reg, bpr+reg}.
+ * grad_out  [N, ld] += dL/d out          (rows of u, p, n; duplicates accumulate)
+ * grad_e0   [N, ld] += alpha0 * dL/d out + (decay/batch) * multiplicity * e0   (may be NULL)
+ * Both gradient buffers must be zero on entry at the rows touched. `touched` (int32
+ * [3*batch], may be NULL) receives the touched row ids so a caller can re-zero sparsely. */
+size_t lgc_bpr_workspace_bytes(int64_t batch);
+int lgc_bpr_loss_grad(int64_t num_nodes, int ld, int64_t batch, const int64_t* users,
+                      const int64_t* pos, const int64_t* neg, const float* out, const float* e0,
+                      double decay, float alpha0, float* grad_out, float* grad_e0, int32_t* touched,
+                      float* loss3, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ Adam (src/train_lightgcn.py:58,147)
+ * torch.optim.Adam defaults (no weight decay, no amsgrad), dense over `n` contiguous floats,
+ * single pass: reads p, g, m, v; writes p, m, v. `step` is the 1-based step count. Hyper-
+ * parameters are doubles (Python floats in the reference) and rounded to fp32 where torch does. */
+int lgc_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr, double beta1,
+                  double beta2, double eps, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------ fused training step
+ * One iteration of `mini_batch_loop` (src/train_lightgcn.py:129-151) for pre-sampled triples:
+ * K-layer forward, BPR + L2, K-layer backward (Horner form on the symmetric operator) with the
+ * dense Adam update fused into the epilogue of the last backward layer. Requires a symmetric
+ * graph. e0, m, v: [N, ld], updated in place. */
+typedef struct {
+  int32_t ld;
+  int32_t num_layers;
+  const float* h_alpha;   /* host, K+1 */
+  int64_t batch;
+  const int64_t* users;
+  const int64_t* pos;
+  const int64_t* neg;
+  double decay;
+  double lr, beta1, beta2, eps;
+  int64_t step;           /* 1-based Adam step */
+  float* e0;
+  float* m;
+  float* v;
+  float* loss3;           /* device, 3 floats */
+  void* workspace;
+  size_t workspace_bytes;
+} lgc_train_step_args;
+size_t lgc_train_step_workspace_bytes(const lgc_graph_t* graph, int ld, int num_layers,
+                                      int64_t batch);
+/* Call once after allocating the workspace (zeroes the two sparse-gradient tables; every step
+ * leaves them zero again). */
+int lgc_train_workspace_init(const lgc_graph_t* graph, int ld, int num_layers, int64_t batch,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int lgc_train_step(const lgc_graph_t* graph, const lgc_train_step_args* args, void* stream);
+
+/* ------------------------------------------------------------------ recommendK (src/lightgcn.py:169-182)
+ * Top-k items for a list of users from the final embeddings:
+ *   pred = user_emb[user_ids] @ item_emb^T                      (src/lightgcn.py:173)
+ *   masked = pred * (1 - seen)   -- MULTIPLICATIVE mask: a seen item scores 0.0, not -inf (:175)
+ *   top-k indices of every row                                   (:177)
+ * The score matrix never reaches HBM: a tcgen05/TMEM fp16 GEMM (fp32 accumulate) keeps only the
+ * maximum of every group of 16 consecutive items; the candidate groups that can hold a top-k
+ * item (with a proven error margin) are re-scored exactly in fp32 with the mask applied, and a
+ * user whose margin cannot be proven is re-scored against all items. Results equal the fp32
+ * reference apart from exact ties / fp32 summation-order near-ties.
+ * seen_ptr/seen_items: CSR over the scored users (row i belongs to user_ids[i]) of un-offset item
+ * ids -- the sparse form of the dense `interactions_t` rows (src/utils_v2.py:92-103,137-138);
+ * NULL = nothing seen. user_ids NULL = users 0..n_users-1.
+ * stats (device, 4 x int64, may be NULL): {users re-scored exhaustively, candidate groups total,
+ * 0, 0}. */
+typedef struct {
+  int32_t d;               /* embedding dim actually used (<= ld_user, ld_item)              */
+  int32_t ld_user;         /* floats per row of user_emb                                     */
+  int32_t ld_item;         /* floats per row of item_emb                                     */
+  int32_t k;               /* 1..32                                                          */
+  int64_t n_users;         /* users to score                                                 */
+  int64_t n_items;
+  const float* user_emb;   /* table the user ids index into                                  */
+  const float* item_emb;   /* [n_items, ld_item]                                             */
+  const int64_t* user_ids; /* [n_users] or NULL                                              */
+  const int64_t* seen_ptr; /* [n_users + 1] or NULL                                          */
+  const int64_t* seen_items;
+  int64_t* topk_items;     /* [n_users, k] out, item ids 0..n_items-1, best first            */
+  float* topk_scores;      /* [n_users, k] out, masked fp32 scores (may be NULL)             */
+  int64_t* stats;          /* [4] out or NULL                                                */
+  void* workspace;
+  size_t workspace_bytes;
+} lgc_score_topk_args;
+size_t lgc_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int d, int k);
+int lgc_score_topk(const lgc_score_topk_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGC_B200_H */

@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): integer / index work and the fp32 degree
+normalisation bit-exact; embeddings, losses and gradients within 1e-5 max-norm relative of the
+fp32 reference; post-Adam weights judged against the fp64 reference with the reference's own
+fp32-vs-fp64 error as the budget (Adam amplifies last-bit gradient noise, hard part 4).
+"""
+import numpy as np
+import pytest
+import torch
+
+from gnn_ecommerce_b200 import synth
+from oracle import port
+from oracle.lgconv import LGConv as OracleLGConv
+
+pytestmark = pytest.mark.gpu
+
+LR, DECAY = 0.005, 1e-4
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _c1_inputs(z):
+    g = synth.make_config_graph("c1")
+    dim, layers = int(z["dim"]), int(z["layers"])
+    bound = np.sqrt(6.0 / (g.num_nodes + dim))
+    init = np.random.default_rng(int(z["init_seed"])).uniform(-bound, bound, (g.num_nodes, dim)).astype(np.float32)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    return g, dim, layers, init, ei, ew
+
+
+def _model(num_nodes, dim, layers, init):
+    from gnn_ecommerce_b200 import LightGCN
+    model = LightGCN(num_nodes, dim, layers)
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(init))
+    return model.to(DEV)
+
+
+# --------------------------------------------------------------------------- graph build
+def test_graph_build_is_bit_exact(golden_c1):
+    from gnn_ecommerce_b200.graph import Graph
+    g, _, _, _, ei, ew = _c1_inputs(golden_c1)
+    gr = Graph(ei.to(DEV), ew.to(DEV), g.num_nodes)
+    a = {k: v.cpu().numpy() for k, v in gr.arrays().items()}
+    csr = port.csr_by_target(ei.numpy(), ew.numpy(), g.num_nodes)
+    assert np.array_equal(a["rowptr"], csr["rowptr"])
+    assert np.array_equal(a["src"], csr["src"])
+    assert np.array_equal(a["eid"], csr["eid"])                 # stable: edge order kept per row
+    assert np.array_equal(a["deg"], csr["deg"]) and np.array_equal(a["deg"], golden_c1["deg"])
+    assert np.array_equal(a["dis"], csr["dis"]) and np.array_equal(a["dis"], golden_c1["dis"])
+    assert np.array_equal(a["w_hat"], csr["w_hat_csr"])
+    assert np.array_equal(gr.w_hat_edge_order().cpu().numpy(), csr["w_hat_edge"])
+    assert gr.is_symmetric
+    assert np.array_equal(np.diff(a["rowptr"]), golden_c1["count_deg"])
+
+
+def test_graph_build_edge_cases():
+    from gnn_ecommerce_b200.graph import Graph
+    # isolated nodes, duplicate edges, a self loop, no weights, non-symmetric
+    ei = torch.tensor([[0, 0, 1, 2, 2, 5], [1, 1, 0, 2, 0, 0]], device=DEV)
+    gr = Graph(ei, None, 8)
+    a = {k: v.cpu().numpy() for k, v in gr.arrays().items()}
+    csr = port.csr_by_target(ei.cpu().numpy(), np.ones(6, np.float32), 8)
+    for k in ("rowptr", "src", "eid", "deg", "dis"):
+        assert np.array_equal(a[k], csr[k]), k
+    assert np.array_equal(a["w_hat"], csr["w_hat_csr"])
+    assert not gr.is_symmetric
+    assert a["dis"][3] == 0 and a["dis"][7] == 0
+    # empty graph
+    g0 = Graph(torch.zeros(2, 0, dtype=torch.int64, device=DEV), None, 5)
+    assert g0.nnz == 0 and np.array_equal(g0.arrays()["rowptr"].cpu().numpy(), np.zeros(6, np.int32))
+    # out-of-range index -> error code, not a device assert
+    with pytest.raises(RuntimeError, match="outside"):
+        Graph(torch.tensor([[0, 9], [1, 0]], device=DEV), None, 4)
+
+
+# --------------------------------------------------------------------------- LGConv operator seam
+@pytest.mark.parametrize("dim", [16, 64, 80, 90, 128])
+def test_lgconv_forward_backward_vs_oracle(dim):
+    from gnn_ecommerce_b200 import LGConv
+    g = synth.make_graph(3000, 400, 40_000, seed=3)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    x = torch.randn(g.num_nodes, dim, generator=torch.Generator().manual_seed(1))
+    xo = x.clone().requires_grad_(True)
+    yo = OracleLGConv()(xo, ei, ew)
+    go = torch.randn(yo.shape, generator=torch.Generator().manual_seed(2))
+    yo.backward(go)
+    xg = x.to(DEV).requires_grad_(True)
+    yg = LGConv()(xg, ei.to(DEV), ew.to(DEV))
+    yg.backward(go.to(DEV))
+    assert yg.shape == yo.shape
+    assert rel(yg.detach().cpu(), yo.detach()) < 1e-5
+    assert rel(xg.grad.cpu(), xo.grad) < 1e-5
+
+
+def test_lgconv_nonsymmetric_backward_uses_transpose():
+    from gnn_ecommerce_b200 import LGConv
+    rng = np.random.default_rng(5)
+    n, nnz, dim = 500, 6000, 32
+    ei = torch.from_numpy(rng.integers(0, n, size=(2, nnz)))
+    ew = torch.from_numpy(rng.choice(synth.WEIGHT_VALUES, nnz))
+    x = torch.randn(n, dim, generator=torch.Generator().manual_seed(1))
+    xo = x.clone().requires_grad_(True)
+    yo = OracleLGConv()(xo, ei, ew)
+    yo.square().sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    yg = LGConv()(xg, ei.to(DEV), ew.to(DEV))
+    yg.square().sum().backward()
+    assert rel(yg.detach().cpu(), yo.detach()) < 1e-5
+    assert rel(xg.grad.cpu(), xo.grad) < 1e-5
+
+
+def test_hub_rows_split_across_warps():
+    """A star: one item with 5000 in-edges (multi-chunk two-phase path) + light rows."""
+    from gnn_ecommerce_b200 import LGConv
+    from gnn_ecommerce_b200.graph import graph_for
+    n_users = 5000
+    u = np.arange(n_users, dtype=np.int64)
+    it = np.full(n_users, n_users, dtype=np.int64)
+    it[::7] = n_users + 1 + (u[::7] % 40)                      # some medium rows (deg ~ 18)
+    w = np.random.default_rng(0).choice(synth.WEIGHT_VALUES, n_users).astype(np.float32)
+    ei, ew = port.df_to_graph(u, it, w)
+    n = n_users + 41
+    x = torch.randn(n, 64, generator=torch.Generator().manual_seed(1))
+    yo = OracleLGConv()(x, ei, ew)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    yg = LGConv()(x.to(DEV), eig, ewg)
+    info = graph_for(eig, ewg, n).info
+    assert info.num_split_rows >= 1 and info.num_chunks > info.num_split_rows
+    assert rel(yg.cpu(), yo) < 1e-5
+
+
+# --------------------------------------------------------------------------- get_embedding / forward
+def test_get_embedding_matches_golden_c1(golden_c1):
+    z = golden_c1
+    g, dim, layers, init, ei, ew = _c1_inputs(z)
+    model = _model(g.num_nodes, dim, layers, init)
+    with torch.no_grad():
+        out = model.get_embedding(ei.to(DEV), ew.to(DEV)).cpu().numpy()
+    assert out.shape == (g.num_nodes, dim)
+    assert rel(out[z["rows"]], z["f32_out0_rows"]) < 1e-5
+    assert rel(out[z["rows"]], z["f64_out0_rows"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["", "iso_"])
+def test_get_embedding_matches_golden_tiny(golden_tiny, tag):
+    z = golden_tiny
+    n = int(z["num_nodes_iso"]) if tag else int(z["n_users"]) + int(z["n_items"])
+    init = z["init_iso"] if tag else z["init"]
+    model = _model(n, int(z["dim"]), int(z["layers"]), init)
+    ei, ew = torch.from_numpy(z["edge_index"]).to(DEV), torch.from_numpy(z["edge_weight"]).to(DEV)
+    with torch.no_grad():
+        out = model.get_embedding(ei, ew).cpu().numpy()
+    assert rel(out, z[f"f32_{tag}out0"]) < 1e-5
+    if tag:   # isolated nodes: alpha_0 * E0 exactly, nothing propagated into them
+        assert np.array_equal(out[n - 3:], z["f32_iso_out0"][n - 3:])
+
+
+@pytest.mark.parametrize("dim,layers", [(64, 3), (80, 4), (90, 5), (64, 1), (32, 0)])
+def test_forward_and_autograd_vs_oracle(dim, layers):
+    """README grid of the reference: K in {3,4,5}, d in {64,80,90} (src README.md:61-64)."""
+    g = synth.make_graph(4000, 600, 50_000, seed=9)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    torch.manual_seed(3)
+    om = port.PortLightGCN(g.num_nodes, dim, layers)
+    model = _model(g.num_nodes, dim, layers, om.embedding.weight.detach().numpy())
+    pl = synth.purchase_lists(g)
+    u, p, n = (torch.from_numpy(x) for x in synth.sample_triples(pl, 256, g.n_users, g.n_items,
+                                                                np.random.default_rng(4)))
+    labels = port.batch_pos_neg_edges(u, p, n)
+    so = om(ei, labels, ew)
+    lo = port.bpr_loss(so[:256], so[256:]) + port.regularization_loss(om.embedding.weight, 256, u, p, n, DECAY)
+    lo.backward()
+    sg = model(ei.to(DEV), labels.to(DEV), ew.to(DEV))
+    lg = model.recommendation_loss(sg[:256], sg[256:], 0) * 256 + port.regularization_loss(
+        model.embedding.weight, 256, u.to(DEV), p.to(DEV), n.to(DEV), DECAY)
+    lg.backward()
+    assert rel(sg.detach().cpu(), so.detach()) < 1e-5
+    assert abs(lg.item() - lo.item()) <= 1e-5 * abs(lo.item())
+    assert rel(model.embedding.weight.grad.cpu(), om.embedding.weight.grad) < 1e-5
+
+
+# --------------------------------------------------------------------------- training step
+def _budget(new, f32, f64, floor=1e-6):
+    """err(new, fp64) <= 1.5 * err(reference fp32, fp64) + floor (max-norm relative)."""
+    return rel(new, f64) <= 1.5 * rel(f32, f64) + floor
+
+
+def test_autograd_training_matches_golden_c1(golden_c1):
+    """Drop-in usage: reference loop with torch.optim.Adam, our module underneath."""
+    z = golden_c1
+    g, dim, layers, init, ei, ew = _c1_inputs(z)
+    model = _model(g.num_nodes, dim, layers, init)
+    opt = torch.optim.Adam(model.parameters(), LR)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    rows = z["rows"]
+    for s, t in enumerate(z["triples"]):
+        u, p, n = (torch.from_numpy(np.ascontiguousarray(x)).to(DEV) for x in t)
+        opt.zero_grad()
+        out = model(eig, port.batch_pos_neg_edges(u, p, n), ewg)
+        size = len(u)
+        bpr = model.recommendation_loss(out[:size], out[size:], 0) * size
+        reg = port.regularization_loss(model.embedding.weight, size, u, p, n, DECAY)
+        loss = bpr + reg
+        loss.backward()
+        if s == 0:
+            assert rel(out.detach().cpu(), z["f32_scores0"]) < 1e-5
+            assert rel(model.embedding.weight.grad.cpu().numpy()[rows], z["f32_grad0_rows"]) < 1e-5
+        opt.step()
+        got = np.array([bpr.item(), reg.item(), loss.item()])
+        assert np.allclose(got, z["f32_losses"][s], rtol=1e-5, atol=0)
+        w = model.embedding.weight.detach().cpu().numpy()[rows]
+        assert _budget(w, z[f"f32_w{s + 1}_rows"], z[f"f64_w{s + 1}_rows"])
+
+
+def test_fused_step_matches_golden_c1(golden_c1):
+    from gnn_ecommerce_b200 import FusedBPRTrainer
+    z = golden_c1
+    g, dim, layers, init, ei, ew = _c1_inputs(z)
+    model = _model(g.num_nodes, dim, layers, init)
+    trainer = FusedBPRTrainer(model, lr=LR)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    rows = z["rows"]
+    for s, t in enumerate(z["triples"]):
+        u, p, n = (torch.from_numpy(np.ascontiguousarray(x)).to(DEV) for x in t)
+        loss3 = trainer.step(eig, ewg, u, p, n, DECAY).cpu().numpy()
+        assert np.allclose(loss3, z["f32_losses"][s], rtol=1e-5, atol=0)
+        w = model.embedding.weight.detach().cpu().numpy()[rows]
+        assert _budget(w, z[f"f32_w{s + 1}_rows"], z[f"f64_w{s + 1}_rows"])
+    sd = trainer.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and int(sd["state"][0]["step"]) == 2
+    assert list(model.state_dict().keys()) == ["alpha", "embedding.weight"]
+    assert model.state_dict()["embedding.weight"].shape == (g.num_nodes, dim)
+
+
+@pytest.mark.parametrize("tag", ["", "iso_"])
+def test_fused_step_matches_golden_tiny(golden_tiny, tag):
+    """Duplicate triples (gradients accumulate, L2 counts multiplicity) and isolated nodes."""
+    from gnn_ecommerce_b200 import FusedBPRTrainer
+    z = golden_tiny
+    n = int(z["num_nodes_iso"]) if tag else int(z["n_users"]) + int(z["n_items"])
+    model = _model(n, int(z["dim"]), int(z["layers"]), z["init_iso"] if tag else z["init"])
+    trainer = FusedBPRTrainer(model, lr=LR)
+    ei, ew = torch.from_numpy(z["edge_index"]).to(DEV), torch.from_numpy(z["edge_weight"]).to(DEV)
+    for s, t in enumerate(z["triples"]):
+        u, p, nn_ = (torch.from_numpy(np.ascontiguousarray(x)).to(DEV) for x in t)
+        loss3 = trainer.step(ei, ew, u, p, nn_, DECAY).cpu().numpy()
+        assert np.allclose(loss3, z[f"f32_{tag}losses"][s], rtol=1e-5, atol=0)
+    w = model.embedding.weight.detach().cpu().numpy()
+    assert _budget(w, z[f"f32_{tag}w2"], z[f"f64_{tag}w2"], floor=2e-6)
+
+
+@pytest.mark.parametrize("dim,layers", [(90, 5), (80, 4), (64, 1), (16, 0)])
+def test_fused_step_equals_autograd_path(dim, layers):
+    """Padded storage (d=90 -> 96 floats per row), other depths: fused == autograd + torch Adam."""
+    from gnn_ecommerce_b200 import FusedBPRTrainer
+    g = synth.make_graph(3000, 500, 40_000, seed=13)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    torch.manual_seed(7)
+    init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, dim)).numpy()
+    ma, mf = _model(g.num_nodes, dim, layers, init), _model(g.num_nodes, dim, layers, init)
+    opt, trainer = torch.optim.Adam(ma.parameters(), LR), FusedBPRTrainer(mf, lr=LR)
+    pl = synth.purchase_lists(g)
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+        u, p, n = (torch.from_numpy(x).to(DEV) for x in synth.sample_triples(pl, 200, g.n_users, g.n_items, rng))
+        opt.zero_grad()
+        out = ma(eig, port.batch_pos_neg_edges(u, p, n), ewg)
+        bpr = ma.recommendation_loss(out[:200], out[200:], 0) * 200
+        reg = port.regularization_loss(ma.embedding.weight, 200, u, p, n, DECAY)
+        (bpr + reg).backward()
+        opt.step()
+        loss3 = trainer.step(eig, ewg, u, p, n, DECAY)
+        assert np.allclose(loss3.cpu().numpy(), [bpr.item(), reg.item(), (bpr + reg).item()], rtol=2e-5)
+    wa, wf = ma.embedding.weight.detach().cpu(), mf.embedding.weight.detach().cpu()
+    assert wf.shape == (g.num_nodes, dim)
+    assert rel(wf, wa) < 5e-4           # three Adam steps amplify last-bit gradient differences
+    assert np.median(np.abs(wf.numpy() - wa.numpy())) < 1e-7
+
+
+def test_adam_kernel_in_isolation():
+    """Identical gradients in, torch.optim.Adam (CPU) as the checker: <= 1e-6 (hard part 4a)."""
+    from gnn_ecommerce_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    p = torch.randn(1000, 64, generator=gen) * 1e-2
+    po = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([po], LR)
+    pg, m, v = p.to(DEV), torch.zeros(1000, 64, device=DEV), torch.zeros(1000, 64, device=DEV)
+    for step in range(1, 6):
+        grad = torch.randn(1000, 64, generator=gen) * (1e-6 if step % 2 else 1e-3)
+        grad[::5] = 0
+        po.grad = grad.clone()
+        opt.step()
+        ops.adam_step(pg, grad.to(DEV), m, v, LR, step=step)
+        assert rel(pg.cpu(), po.detach()) < 1e-6
+    st = opt.state[po]
+    assert rel(m.cpu(), st["exp_avg"]) < 1e-6 and rel(v.cpu(), st["exp_avg_sq"]) < 1e-6
+
+
+# --------------------------------------------------------------------------- full size (c2)
+def test_c2_full_size_against_reference_gpu_path():
+    """At BASELINE.json's full size the oracle's LGConv restatement runs on the GPU itself
+    (index_select / mul / scatter_add_ = the reference's own CUDA path), plus size-independent
+    properties: linearity and symmetry <y, A x> = <A y, x>."""
+    from gnn_ecommerce_b200 import LGConv
+    g = synth.make_config_graph("c2")
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    ei, ew = ei.to(DEV), ew.to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(g.num_nodes, 64, device=DEV, generator=gen)
+    y = torch.randn(g.num_nodes, 64, device=DEV, generator=gen)
+    conv = LGConv()
+    ax = conv(x, ei, ew)
+    ref = OracleLGConv()(x, ei, ew)
+    assert rel(ax.cpu(), ref.cpu()) < 1e-5
+    del ref
+    ay = conv(y, ei, ew)
+    lhs, rhs = (y.double() * ax.double()).sum().item(), (ay.double() * x.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs))
+    comb = conv(2.0 * x - 0.5 * y, ei, ew)
+    assert rel(comb.cpu(), (2.0 * ax - 0.5 * ay).cpu()) < 1e-5
