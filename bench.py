@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""Benchmark of the LightGCN hot path (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2]
+
+A "step" is one training mini-batch of `TrainLightGCN.mini_batch_loop`
+(reference `src/train_lightgcn.py:129-151`): K-layer forward over ALL edges, BPR + L2 loss,
+K-layer backward, dense Adam -- on the synthetic Cosmetics-Shop-shaped graph c2
+(1.6 M users x 54 K items, 5 M weighted edges -> nnz = 10 M directed, d = 64, K = 3, batch 1024).
+
+metric `lgconv_gedges_per_s` = nnz * 2K * steps / seconds (directed edges through LGConv layer
+passes, forward + backward). `value` has triples resident in HBM; `e2e` goes
+through the public Python API with pinned host triples copied H2D and the three losses read
+back D2H every step. Also reported: epoch seconds (122 steps), top-20 scoring users/s (c4),
+the roofline of the dominant kernel, and the CPU port of the reference timed on this box.
+
+`--impl reference` times the reference's CPU path (oracle port: the reference's own torch ops;
+real PyG is not installable here) on all host cores: each step = one LGConv layer forward +
+backward over the same c2 graph (a bounded sample: a full CPU step is ~14 s).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH, LR, DECAY = 1024, 0.005, 1e-4       # src/train_lightgcn.py:47-53
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workload
+def make_workload(config: str, n_batches: int):
+    from gnn_ecommerce_b200 import synth
+    t0 = time.time()
+    n_users, n_items, n_edges, dim, layers = synth.CONFIGS[config]
+    g = synth.make_graph(n_users, n_items, n_edges, seed=42)
+    pl = synth.purchase_lists(g)
+    rng = np.random.default_rng(44)
+    triples = [synth.sample_triples(pl, BATCH, g.n_users, g.n_items, rng) for _ in range(n_batches)]
+    bound = np.sqrt(6.0 / (g.num_nodes + dim))            # xavier_uniform_ (src/lightgcn.py:87)
+    init = np.random.default_rng(43).uniform(-bound, bound, (g.num_nodes, dim)).astype(np.float32)
+    log(f"[bench] synthetic {config}: N={g.num_nodes} nnz={2 * g.num_edges} d={dim} K={layers} "
+        f"({time.time() - t0:.1f}s)")
+    return g, dim, layers, init, triples
+
+
+def algorithmic_bytes(g, dim_ld: int, layers: int, nnz: int):
+    """int32 CSR, fp32 values. I = nnz*8 + (N+1)*4, T = N*ld*4,
+    B_prop = K*I + (4K-1)*T, step = 2*B_prop + 7T."""
+    n = g.num_nodes
+    idx = nnz * 8 + (n + 1) * 4
+    t = n * dim_ld * 4
+    b_prop = layers * idx + (4 * layers - 1) * t
+    return {"I": idx, "T": t, "B_prop": b_prop, "step": 2 * b_prop + 7 * t}
+
+
+def light_kernel_bytes(g, graph, ld: int):
+    """Algorithmic bytes of ONE launch of the dominant kernel (k_spmm_light, the sub-warp-per-row
+    pass over rows with in-degree <= 32), averaged over the 6 launches of a K=3 step:
+    indices + weights of the light rows' edges, each distinct gathered source row once, rowptr,
+    plus the epilogue traffic of the light rows (mode dependent)."""
+    a = graph.arrays()
+    rowptr = a["rowptr"].cpu().numpy().astype(np.int64)
+    deg = np.diff(rowptr)
+    light = deg <= graph.info.light_max_degree
+    e_light = int(deg[light].sum())
+    src = a["src"].cpu().numpy()
+    rows_of_entry = np.repeat(np.arange(g.num_nodes), deg)
+    distinct_src = int(np.unique(src[light[rows_of_entry]]).size)
+    rb = ld * 4
+    n_light = int(light.sum())
+    gather = e_light * 8 + (g.num_nodes + 1) * 4 + distinct_src * rb
+    per_mode = {"fwd_init": 3 * rb, "fwd_rmw_store": 3 * rb, "fwd_rmw_last": 2 * rb,
+                "bwd_plain": 2 * rb, "bwd_adam": 7 * rb}
+    # K = 3 step: fwd_init, fwd_rmw(store), fwd_rmw(last), bwd_plain x2, bwd_adam
+    epi = (per_mode["fwd_init"] + per_mode["fwd_rmw_store"] + per_mode["fwd_rmw_last"]
+           + 2 * per_mode["bwd_plain"] + per_mode["bwd_adam"]) / 6.0
+    return {"bytes_per_launch": gather + n_light * epi, "light_rows": n_light,
+            "light_edges": e_light, "distinct_sources": distinct_src}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_full_step(g, dim, layers, init, triple):
+    """One full reference training step on the host cores (oracle port)."""
+    import torch
+    from oracle import port
+    torch.set_num_threads(os.cpu_count() or 1)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    model = port.PortLightGCN(g.num_nodes, dim, layers)
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(init))
+    opt = torch.optim.Adam(model.parameters(), LR)
+    u, p, n = (torch.from_numpy(x) for x in triple)
+    t0 = time.perf_counter()
+    port.train_step(model, opt, ei, ew, u, p, n, DECAY)
+    dt = time.perf_counter() - t0
+    return dt, torch.get_num_threads()
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU arithmetic for the path, all host threads."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import port
+    from oracle.lgconv import LGConv
+    torch.set_num_threads(os.cpu_count() or 1)
+    g, dim, layers, init, _ = make_workload(args.config, 0)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    nnz = ei.size(1)
+    conv = LGConv()
+    x = torch.from_numpy(init).requires_grad_(True)
+
+    def one():
+        x.grad = None
+        conv(x, ei, ew).sum().backward()
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    value = nnz * 2 * args.steps / dt / 1e9
+    sample = (f"one LGConv layer forward+backward per step over the full {args.config} graph "
+              f"(nnz={nnz}, d={dim}); a full K={layers} step is {layers}x this plus Adam")
+    line = {"impl": "reference", "metric": "lgconv_gedges_per_s", "value": value, "unit": "GEdges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: LightGCN K={layers} d={dim}, N={g.num_nodes}, "
+                                   f"nnz={nnz}, batch={BATCH}"},
+            "cpu_baseline": {"value": value, "unit": "GEdges/s", "cores": torch.get_num_threads(),
+                             "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "GEdges/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--score-users", type=int, default=0, help="0 = all users (c4)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from gnn_ecommerce_b200 import FusedBPRTrainer, LightGCN, _capi, scoring
+    from gnn_ecommerce_b200.graph import padded_dim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.lib()
+    pk = peaks()
+
+    n_batches = args.steps + args.warmup
+    g, dim, layers, init, triples = make_workload(args.config, n_batches)
+    nnz = 2 * g.num_edges
+    ld = padded_dim(dim)
+
+    ei = torch.from_numpy(g.edge_index()).to(dev)
+    ew = torch.from_numpy(g.edge_weight()).to(dev)
+    model = LightGCN(g.num_nodes, dim, layers)
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(init))
+    model = model.to(dev)
+    trainer = FusedBPRTrainer(model, lr=LR)
+    graph = model.graph(ei, ew)
+    dev_triples = [tuple(torch.from_numpy(x).to(dev) for x in t) for t in triples]
+    pin_triples = [tuple(torch.from_numpy(x).pin_memory() for x in t) for t in triples]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up + exactly K timed steps (inputs: 1 GB+ of tables,
+    # far larger than the 126 MB L2, so no flush is needed between iterations)
+    for i in range(args.warmup):
+        trainer.step(ei, ew, *dev_triples[i], DECAY)
+    barrier()
+    launches0 = lib.lgc_launch_count()
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        beg.record()
+        for i in range(args.steps):
+            loss3 = trainer.step(ei, ew, *dev_triples[args.warmup + i], DECAY)
+        end.record()
+        barrier()
+    launches = lib.lgc_launch_count() - launches0
+    ms_total = beg.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    last_losses = [float(x) for x in loss3.cpu().tolist()]
+    gedges = nnz * 2 * layers * args.steps * world / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end through the public API: pinned host triples -> H2D, losses -> D2H per step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        u, p, n = (x.to(dev, non_blocking=True) for x in pin_triples[args.warmup + i])
+        host_losses = trainer.step(ei, ew, u, p, n, DECAY).cpu()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_gedges = nnz * 2 * layers * args.steps * world / e2e_s / 1e9
+
+    # ---- per-kernel-class durations (CUDA events on the launching stream) over K more steps
+    n_tags = 24
+    ms_arr, cnt_arr = (C.c_double * n_tags)(), (C.c_longlong * n_tags)()
+    lib.lgc_profile_enable(1)
+    for i in range(args.steps):
+        trainer.step(ei, ew, *dev_triples[args.warmup + i], DECAY)
+    torch.cuda.synchronize()
+    lib.lgc_profile_read(ms_arr, cnt_arr, n_tags)
+    lib.lgc_profile_enable(0)
+    prof = {t: (ms_arr[t], cnt_arr[t]) for t in range(n_tags) if cnt_arr[t]}
+    light_ms = sum(ms_arr[t] for t in range(0, 4))
+    light_cnt = sum(cnt_arr[t] for t in range(0, 4))
+    heavy_ms = sum(ms_arr[t] for t in range(4, 8))
+    finish_ms = sum(ms_arr[t] for t in range(8, 12))
+    kernel_ms_total = sum(ms_arr)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    alg = algorithmic_bytes(g, ld, layers, nnz)
+    lk = light_kernel_bytes(g, graph, ld)
+    light_avg_ms = light_ms / max(light_cnt, 1)
+    achieved = lk["bytes_per_launch"] / (light_avg_ms * 1e-3) / 1e9
+    traffic = None
+    prof_json = os.path.join(ROOT, "profiles", "ncu_light_traffic.json")
+    if os.path.exists(prof_json):
+        try:
+            traffic = float(json.load(open(prof_json))["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_spmm_light", "achieved": achieved, "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                "peak_source": pk["source"], "kernel_ms": light_avg_ms,
+                "kernel_share_of_step": light_ms / max(kernel_ms_total, 1e-9),
+                "algorithmic_bytes_per_launch": lk["bytes_per_launch"],
+                "step_algorithmic_bytes": alg["step"],
+                "step_achieved_gbs": alg["step"] / (ms_step * 1e-3) / 1e9,
+                "step_frac": alg["step"] / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "class_ms_per_step": {"light": light_ms / args.steps, "heavy": heavy_ms / args.steps,
+                                      "finish": finish_ms / args.steps,
+                                      "bpr": ms_arr[12] / args.steps}}
+
+    # ---- scoring (c4): all users x all items, top-20, user table resident
+    score = None
+    if not args.no_scoring:
+        try:
+            score = bench_scoring(model, ei, ew, g, dev, args, pk)
+        except Exception as e:  # a missing kernel must not hide the training number
+            log(f"[bench] scoring failed: {e!r}")
+            score = {"error": repr(e)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        dt, cores = cpu_full_step(g, dim, layers, init, triples[0])
+        cpu = {"value": nnz * 2 * layers / dt / 1e9, "unit": "GEdges/s", "cores": cores, "kind": "port",
+               "sample": f"1 full training step (K={layers} fwd + BPR + bwd + dense Adam) at {args.config} "
+                         f"shape, {dt:.1f} s, oracle port of the reference's torch ops",
+               "step_s": dt}
+
+    steps_per_epoch = int(g.num_edges / (BATCH * 40))        # src/train_lightgcn.py:92
+    line = {
+        "metric": "lgconv_gedges_per_s", "value": gedges, "unit": "GEdges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: LightGCN K={layers} d={dim}, N={g.num_nodes}, nnz={nnz}, "
+                               f"batch={BATCH}, full training step (fwd+BPR+bwd+Adam)",
+                   "l2": "inputs (>=1 GB of tables per step) exceed the 126 MB L2; no flush",
+                   "steps_per_epoch": steps_per_epoch},
+        "epoch_s": ms_step * steps_per_epoch * 1e-3,
+        "losses_last_step": last_losses,
+        "e2e": {"value": e2e_gedges, "unit": "GEdges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
+                "d2h_bytes_per_step": 12, "ms_per_step": e2e_s / args.steps * 1e3,
+                "losses_last_step": [float(x) for x in host_losses.tolist()]},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "scoring": score,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_scoring(model, ei, ew, g, dev, args, pk):
+    import torch
+    from gnn_ecommerce_b200 import ops, scoring, synth
+    k = 20
+    with torch.no_grad():
+        emb = model.get_embedding(ei, ew)
+    rows = ops.full_rows(emb)
+    n_score = args.score_users or g.n_users
+    users = torch.arange(n_score, device=dev)
+    ptr, items = synth.seen_lists(g, np.arange(n_score))
+    seen = scoring.SeenLists.from_numpy(ptr, items, dev)
+    user_t, item_t = rows[:g.n_users], rows[g.n_users:]
+
+    def run():
+        return scoring.score_topk(user_t, item_t, users, seen.ptr, seen.items, k,
+                                  d=model.embedding_dim, return_stats=True)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    beg.record()
+    for _ in range(reps):
+        top, sc, stats = run()
+    end.record()
+    torch.cuda.synchronize()
+    ms = beg.elapsed_time(end) / reps
+    flops = 2.0 * n_score * g.n_items * model.embedding_dim
+    tf = flops / (ms * 1e-3) / 1e12
+    st = stats.cpu().tolist()
+    return {"metric": "top20_users_per_s", "value": n_score / (ms * 1e-3), "unit": "users/s",
+            "users": n_score, "items": g.n_items, "k": k, "ms": ms,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
+                         "peak_source": pk["source"]},
+            "fallback_users": st[0], "candidate_groups": st[1]}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

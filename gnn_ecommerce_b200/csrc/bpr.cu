@@ -147,6 +147,7 @@ int bpr_launch(int64_t num_nodes, int ld, int64_t batch, const int64_t* users, c
                int* bad, cudaStream_t st) {
   const int threads = 256;
   const int grid = (int)ceil_div(batch * 32, threads);
+  ProfScope ps(PROF_BPR, st);
   k_bpr<<<grid, threads, 0, st>>>(num_nodes, ld, batch, users, pos, neg, out, e0,
                                   (float)(1.0 / (double)batch), (float)(decay / (double)batch), alpha0,
                                   grad_out, grad_e0, touched, per_triple, bad);

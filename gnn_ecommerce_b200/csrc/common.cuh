@@ -30,7 +30,33 @@ void set_error(const std::string& msg);
     }                                                                                    \
   } while (0)
 
-#define LGC_LAUNCH_CHECK() LGC_CUDA(cudaGetLastError())
+extern long long g_launch_count;   // kernels launched by this library (claim for bench.py)
+#define LGC_LAUNCH_CHECK()              \
+  do {                                  \
+    ++::lgc::g_launch_count;            \
+    LGC_CUDA(cudaGetLastError());       \
+  } while (0)
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py only).
+enum ProfTag : int {
+  PROF_LIGHT = 0,    // + EpiMode
+  PROF_HEAVY = 4,    // + EpiMode
+  PROF_FINISH = 8,   // + EpiMode
+  PROF_BPR = 12,
+  PROF_MISC = 13,
+  PROF_SCORE_CONVERT = 16,
+  PROF_SCORE_GEMM = 17,
+  PROF_SCORE_SELECT = 18,
+  PROF_SCORE_RESCORE = 19,
+  PROF_NUM_TAGS = 24
+};
+bool prof_enabled();
+void prof_record(int tag, cudaStream_t st, bool begin);
+struct ProfScope {
+  int tag; cudaStream_t st; bool on;
+  ProfScope(int t, cudaStream_t s) : tag(t), st(s), on(prof_enabled()) { if (on) prof_record(tag, st, true); }
+  ~ProfScope() { if (on) prof_record(tag, st, false); }
+};
 
 constexpr int kNumSMs = 148;  // B200
 

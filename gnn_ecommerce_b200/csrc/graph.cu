@@ -3,12 +3,32 @@
 // (reference call site src/lightgcn.py:96; input layout src/utils_v2.py:146-165).
 #include <cub/cub.cuh>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace lgc {
 
 thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+long long g_launch_count = 0;
+
+struct ProfEvent { int tag; cudaEvent_t beg, end; };
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_events;
+bool prof_enabled() { return g_prof_on; }
+void prof_record(int tag, cudaStream_t st, bool begin) {
+  if (begin) {
+    ProfEvent e; e.tag = tag;
+    cudaEventCreate(&e.beg); cudaEventCreate(&e.end);
+    cudaEventRecord(e.beg, st);
+    g_prof_events.push_back(e);
+  } else {
+    for (size_t i = g_prof_events.size(); i-- > 0;)
+      if (g_prof_events[i].tag == tag) { cudaEventRecord(g_prof_events[i].end, st); break; }
+  }
+}
 
 namespace {
 
@@ -143,6 +163,29 @@ using namespace lgc;
 
 extern "C" int lgc_abi_version(void) { return LGC_ABI_VERSION; }
 extern "C" const char* lgc_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" long long lgc_launch_count(void) { return g_launch_count; }
+
+extern "C" int lgc_profile_enable(int on) {
+  for (auto& e : g_prof_events) { cudaEventDestroy(e.beg); cudaEventDestroy(e.end); }
+  g_prof_events.clear();
+  g_prof_on = on != 0;
+  return LGC_OK;
+}
+
+extern "C" int lgc_profile_read(double* h_ms, long long* h_count, int n_tags) {
+  LGC_REQUIRE(h_ms && h_count && n_tags > 0, "bad argument");
+  for (int i = 0; i < n_tags; ++i) { h_ms[i] = 0.0; h_count[i] = 0; }
+  for (auto& e : g_prof_events) {
+    LGC_CUDA(cudaEventSynchronize(e.end));
+    float ms = 0.f;
+    LGC_CUDA(cudaEventElapsedTime(&ms, e.beg, e.end));
+    if (e.tag >= 0 && e.tag < n_tags) { h_ms[e.tag] += ms; h_count[e.tag] += 1; }
+    cudaEventDestroy(e.beg); cudaEventDestroy(e.end);
+  }
+  g_prof_events.clear();
+  return LGC_OK;
+}
 
 extern "C" int lgc_graph_destroy(lgc_graph_t* g) {
   if (!g) return LGC_OK;

@@ -211,19 +211,28 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   const int threads = 256, wpb = threads / 32;
   const int64_t n = g->num_nodes;
   const int grid_light = (int)ceil_div(ceil_div(n, RPW), wpb);
-  k_spmm_light<L, V, MODE><<<grid_light, threads, 0, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
-                                                            g->light_max_degree, a);
+  {
+    ProfScope ps(PROF_LIGHT + MODE, st);
+    k_spmm_light<L, V, MODE><<<grid_light, threads, 0, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
+                                                              g->light_max_degree, a);
+  }
   LGC_LAUNCH_CHECK();
   if (g->num_chunks > 0) {
     const int grid_heavy = (int)ceil_div(g->num_chunks, wpb);
-    k_spmm_heavy<L, V, MODE><<<grid_heavy, threads, 0, st>>>(g->chunks, (int)g->num_chunks, g->src,
-                                                              g->w_hat, x, partials, a);
+    {
+      ProfScope ps(PROF_HEAVY + MODE, st);
+      k_spmm_heavy<L, V, MODE><<<grid_heavy, threads, 0, st>>>(g->chunks, (int)g->num_chunks, g->src,
+                                                                g->w_hat, x, partials, a);
+    }
     LGC_LAUNCH_CHECK();
   }
   if (g->num_split_rows > 0) {
     const int grid_fin = (int)ceil_div(ceil_div(g->num_split_rows, RPW), wpb);
-    k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, st>>>(g->split_rows, (int)g->num_split_rows,
-                                                             partials, a);
+    {
+      ProfScope ps(PROF_FINISH + MODE, st);
+      k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, st>>>(g->split_rows, (int)g->num_split_rows,
+                                                               partials, a);
+    }
     LGC_LAUNCH_CHECK();
   }
   return LGC_OK;

@@ -40,8 +40,8 @@ def pad_table(x: Tensor) -> Tensor:
     if (x.dim() == 2 and x.stride(1) == 1 and x.stride(0) == ld and x.data_ptr() % 16 == 0
             and (ld == x.size(1) or _pad_is_zero_view(x, ld))):
         return x
-    out = torch.zeros(x.size(0), ld, dtype=torch.float32, device=x.device)
-    out[:, :x.size(1)] = x
+    out = new_table(x.size(0), x.size(1), x.device)     # [N, d] view of a zeroed [N, ld] table
+    out.copy_(x)
     return out
 
 

@@ -49,6 +49,16 @@ const char* lgc_last_error(void);
 /* 1 if `ld` (floats per table row) has a kernel instantiation, else 0. */
 int lgc_ld_supported(int ld);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional
+ * per-kernel-class timing with CUDA events recorded on the launching stream around each launch.
+ * Tags: 0-3 light-row SpMM by epilogue {plain, fwd-init, fwd-rmw, adam}, 4-7 heavy-row SpMM,
+ * 8-11 split-row finish, 12 BPR, 13 misc, 16-19 scoring {convert, gemm, select, rescore}.
+ * lgc_profile_read synchronises the recorded events, sums milliseconds and launch counts per tag
+ * into the HOST arrays and clears the record. */
+long long lgc_launch_count(void);
+int lgc_profile_enable(int on);
+int lgc_profile_read(double* h_ms, long long* h_count, int n_tags);
+
 /* ------------------------------------------------------------------ graph build (once per graph)
  * Replaces what PyG `gcn_norm` recomputes inside EVERY LGConv.forward call (K times per step;
  * call site src/lightgcn.py:96) on the edge list produced by `df_to_graph`
