@@ -17,104 +17,179 @@
 namespace lgc {
 namespace {
 
+// Operands of the epilogue that do not depend on the SpMM sum: loaded BEFORE the gathers so
+// their latency overlaps the gather latency instead of following it.
+struct Pre {
+  float4 r0, r1, r2, r3;
+};
+
 template <int MODE>
-__device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s) {
+__device__ __forceinline__ void epi_preload(const EpiArgs& a, size_t off, Pre& p) {
+  if (MODE == EPI_PLAIN) {
+    if (a.addend) p.r0 = ldg_f4(a.addend + off);
+  } else if (MODE == EPI_FWD_INIT) {
+    p.r0 = ldg_f4(a.xrow + off);
+  } else if (MODE == EPI_FWD_RMW) {
+    p.r0 = ld_f4_cs(a.acc + off);
+  } else {  // EPI_ADAM
+    p.r0 = ld_f4_cs(a.addend + off);
+    p.r1 = ld_f4(a.p + off);
+    p.r2 = ld_f4_cs(a.m + off);
+    p.r3 = ld_f4_cs(a.v + off);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_finish(const EpiArgs& a, size_t off, float4 s, const Pre& q) {
   if (MODE == EPI_PLAIN) {
     float4 r = make_float4(a.scale * s.x, a.scale * s.y, a.scale * s.z, a.scale * s.w);
     if (a.addend) {
-      float4 g = ldg_f4(a.addend + off);
-      r.x = fmaf(a.beta, g.x, r.x); r.y = fmaf(a.beta, g.y, r.y);
-      r.z = fmaf(a.beta, g.z, r.z); r.w = fmaf(a.beta, g.w, r.w);
+      r.x = fmaf(a.beta, q.r0.x, r.x); r.y = fmaf(a.beta, q.r0.y, r.y);
+      r.z = fmaf(a.beta, q.r0.z, r.z); r.w = fmaf(a.beta, q.r0.w, r.w);
     }
     st_f4(a.y + off, r);
   } else if (MODE == EPI_FWD_INIT) {
     if (a.y) st_f4(a.y + off, s);
-    float4 x = ldg_f4(a.xrow + off), r;   // out = x * alpha0; out = out + x1 * alpha1
-    r.x = __fadd_rn(__fmul_rn(x.x, a.a0), __fmul_rn(s.x, a.a1));
-    r.y = __fadd_rn(__fmul_rn(x.y, a.a0), __fmul_rn(s.y, a.a1));
-    r.z = __fadd_rn(__fmul_rn(x.z, a.a0), __fmul_rn(s.z, a.a1));
-    r.w = __fadd_rn(__fmul_rn(x.w, a.a0), __fmul_rn(s.w, a.a1));
+    float4 r;                              // out = x * alpha0; out = out + x1 * alpha1
+    r.x = __fadd_rn(__fmul_rn(q.r0.x, a.a0), __fmul_rn(s.x, a.a1));
+    r.y = __fadd_rn(__fmul_rn(q.r0.y, a.a0), __fmul_rn(s.y, a.a1));
+    r.z = __fadd_rn(__fmul_rn(q.r0.z, a.a0), __fmul_rn(s.z, a.a1));
+    r.w = __fadd_rn(__fmul_rn(q.r0.w, a.a0), __fmul_rn(s.w, a.a1));
     st_f4_cs(a.acc + off, r);
   } else if (MODE == EPI_FWD_RMW) {
     if (a.y) st_f4(a.y + off, s);
-    float4 o = ld_f4_cs(a.acc + off);
+    float4 o = q.r0;
     o.x = __fadd_rn(o.x, __fmul_rn(s.x, a.a1)); o.y = __fadd_rn(o.y, __fmul_rn(s.y, a.a1));
     o.z = __fadd_rn(o.z, __fmul_rn(s.z, a.a1)); o.w = __fadd_rn(o.w, __fmul_rn(s.w, a.a1));
     st_f4_cs(a.acc + off, o);
   } else {  // EPI_ADAM
-    float4 z = ld_f4_cs(a.addend + off);
-    float4 p = ld_f4(a.p + off), m = ld_f4_cs(a.m + off), v = ld_f4_cs(a.v + off);
-    adam_update(p.x, m.x, v.x, fmaf(a.scale, s.x, z.x), a.adam);
-    adam_update(p.y, m.y, v.y, fmaf(a.scale, s.y, z.y), a.adam);
-    adam_update(p.z, m.z, v.z, fmaf(a.scale, s.z, z.z), a.adam);
-    adam_update(p.w, m.w, v.w, fmaf(a.scale, s.w, z.w), a.adam);
+    float4 p = q.r1, m = q.r2, v = q.r3;
+    adam_update(p.x, m.x, v.x, fmaf(a.scale, s.x, q.r0.x), a.adam);
+    adam_update(p.y, m.y, v.y, fmaf(a.scale, s.y, q.r0.y), a.adam);
+    adam_update(p.z, m.z, v.z, fmaf(a.scale, s.z, q.r0.z), a.adam);
+    adam_update(p.w, m.w, v.w, fmaf(a.scale, s.w, q.r0.w), a.adam);
     st_f4(a.p + off, p);
     st_f4_cs(a.m + off, m);
     st_f4_cs(a.v + off, v);
   }
 }
 
+template <int MODE>
+__device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s) {
+  Pre q;
+  epi_preload<MODE>(a, off, q);
+  epi_finish<MODE>(a, off, s, q);
+}
+
 // ---------------------------------------------------------------------------------- light rows
+// One CTA = a tile of consecutive rows. The tile's rowptr slice and (when it fits) its contiguous
+// CSR slice of (source, weight) pairs are staged in shared memory with two coalesced rounds, so a
+// row costs ONE exposed memory latency (its gathers, issued together with its epilogue operands)
+// instead of four dependent ones (rowptr -> indices -> gathers -> epilogue operands). Each L-lane
+// sub-warp walks its rows two at a time to double the loads in flight.
+constexpr int kLightRowsPerSub = 8;
+constexpr int kLightStageCap = 2048;   // staged CSR entries per tile (16 KB)
+
 template <int L, int V, int MODE>
 __global__ void __launch_bounds__(256) k_spmm_light(const int32_t* __restrict__ rowptr,
                                                     const int32_t* __restrict__ src,
                                                     const float* __restrict__ w,
                                                     const float* __restrict__ x, int num_rows,
                                                     int light_max, EpiArgs args) {
-  constexpr int RPW = 32 / L;        // rows per warp
   constexpr int LD = 4 * L * V;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane / L, sl = lane % L;
-  const unsigned sub_mask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t row = warp * RPW + sub;
-  if (row >= num_rows) return;
-  const int beg = rowptr[row], end = rowptr[row + 1];
-  if (end - beg > light_max) return;  // heavy path owns this row
+  constexpr int NSUB = 256 / L;                       // sub-warps per CTA
+  constexpr int TILE = NSUB * kLightRowsPerSub;       // rows per CTA
+  __shared__ int s_rp[TILE + 1];
+  __shared__ int s_src[kLightStageCap];
+  __shared__ float s_w[kLightStageCap];
 
-  float4 acc[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int row0 = blockIdx.x * TILE;
+  for (int t = threadIdx.x; t <= TILE; t += 256) s_rp[t] = rowptr[min(row0 + t, num_rows)];
+  __syncthreads();
+  const int e0 = s_rp[0], n_e = s_rp[TILE] - e0;
+  const bool staged = n_e <= kLightStageCap;
+  if (staged) {
+    for (int i = threadIdx.x; i < n_e; i += 256) { s_src[i] = src[e0 + i]; s_w[i] = w[e0 + i]; }
+  }
+  __syncthreads();
 
-  for (int base = beg; base < end; base += L) {
-    // one coalesced load brings up to L (source, weight) pairs of this row
-    int my_s = 0; float my_w = 0.f;
-    if (base + sl < end) { my_s = src[base + sl]; my_w = w[base + sl]; }
-    const int n = min(L, end - base);
-    for (int j0 = 0; j0 < n; j0 += 4) {
-      int s[4]; float ww[4]; float4 xv[4][V];
+  const int sw = threadIdx.x / L, sl = threadIdx.x % L;
+#pragma unroll 1
+  for (int j = 0; j < kLightRowsPerSub; j += 2) {
+    // consecutive sub-warps take consecutive rows: a warp's stores are contiguous
+    const int ta = j * NSUB + sw, tb = ta + NSUB;
+    const int rowa = row0 + ta, rowb = row0 + tb;
+    int bega = s_rp[ta], dega = s_rp[ta + 1] - bega;
+    int begb = s_rp[tb], degb = s_rp[tb + 1] - begb;
+    const bool oka = rowa < num_rows && dega <= light_max;
+    const bool okb = rowb < num_rows && degb <= light_max;
+    if (!oka) dega = 0;
+    if (!okb) degb = 0;
+    const size_t offa = (size_t)rowa * LD + 4 * sl, offb = (size_t)rowb * LD + 4 * sl;
+    Pre qa[V], qb[V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        s[u] = __shfl_sync(sub_mask, my_s, sub * L + ((j0 + u) & (L - 1)));
-        ww[u] = __shfl_sync(sub_mask, my_w, sub * L + ((j0 + u) & (L - 1)));
+    for (int v = 0; v < V; ++v) {
+      if (oka) epi_preload<MODE>(args, offa + 4 * L * v, qa[v]);
+      if (okb) epi_preload<MODE>(args, offb + 4 * L * v, qb[v]);
+    }
+    float4 acca[V], accb[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acca[v] = accb[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int dmax = max(dega, degb);
+    for (int t = 0; t < dmax; t += 2) {
+      int sa[2], sb[2]; float wa[2], wb[2]; float4 xa[2][V], xb[2][V];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (t + u < dega) {
+          const int e = bega + t + u;
+          sa[u] = staged ? s_src[e - e0] : src[e];
+          wa[u] = staged ? s_w[e - e0] : w[e];
+        }
+        if (t + u < degb) {
+          const int e = begb + t + u;
+          sb[u] = staged ? s_src[e - e0] : src[e];
+          wb[u] = staged ? s_w[e - e0] : w[e];
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (j0 + u < n) {
-          const float* xr = x + (size_t)s[u] * LD + 4 * sl;
+      for (int u = 0; u < 2; ++u) {
+        if (t + u < dega) {
+          const float* xr = x + (size_t)sa[u] * LD + 4 * sl;
 #pragma unroll
-          for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+          for (int v = 0; v < V; ++v) xa[u][v] = ldg_f4(xr + 4 * L * v);
         }
+        if (t + u < degb) {
+          const float* xr = x + (size_t)sb[u] * LD + 4 * sl;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (j0 + u < n) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = fma4(ww[u], xv[u][v], acc[v]);
+          for (int v = 0; v < V; ++v) xb[u][v] = ldg_f4(xr + 4 * L * v);
         }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (t + u < dega) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acca[v] = fma4(wa[u], xa[u][v], acca[v]);
+        }
+        if (t + u < degb) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) accb[v] = fma4(wb[u], xb[u][v], accb[v]);
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (oka) epi_finish<MODE>(args, offa + 4 * L * v, acca[v], qa[v]);
+      if (okb) epi_finish<MODE>(args, offb + 4 * L * v, accb[v], qb[v]);
     }
   }
-  const size_t off = (size_t)row * LD + 4 * sl;
-#pragma unroll
-  for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
 }
 
 // ---------------------------------------------------------------------------------- heavy rows
 template <int L, int V, int MODE>
-__global__ void __launch_bounds__(256) k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks,
-                                                    const int32_t* __restrict__ src,
-                                                    const float* __restrict__ w,
-                                                    const float* __restrict__ x,
-                                                    float* __restrict__ partials, EpiArgs args) {
+__global__ void __launch_bounds__(256, (V == 1) ? 3 : 2)
+k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks, const int32_t* __restrict__ src,
+             const float* __restrict__ w, const float* __restrict__ x, float* __restrict__ partials,
+             EpiArgs args) {
   constexpr int RPW = 32 / L;        // edge streams per warp
   constexpr int LD = 4 * L * V;
   constexpr int U = (L >= 8) ? 8 : L;  // gathers in flight per stream and unrolled step
@@ -136,20 +211,18 @@ __global__ void __launch_bounds__(256) k_spmm_heavy(const int4* __restrict__ chu
     // stream `sub` takes entries sub, sub+RPW, ... of this block of 32
 #pragma unroll
     for (int t0 = 0; t0 < L; t0 += U) {
-      int s[U]; float ww[U]; float4 xv[U][V];
+      float ww[U]; float4 xv[U][V];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int idx = (t0 + u) * RPW + sub;
-        s[u] = __shfl_sync(0xffffffffu, my_s, idx);
+        const int s = __shfl_sync(0xffffffffu, my_s, idx);
         ww[u] = __shfl_sync(0xffffffffu, my_w, idx);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if ((t0 + u) * RPW + sub < n) {
-          const float* xr = x + (size_t)s[u] * LD + 4 * sl;
+        if (idx < n) {
+          const float* xr = x + (size_t)s * LD + 4 * sl;
 #pragma unroll
           for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
         }
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if ((t0 + u) * RPW + sub < n) {
@@ -181,24 +254,33 @@ __global__ void __launch_bounds__(256) k_spmm_heavy(const int4* __restrict__ chu
   }
 }
 
+// One CTA per split row: 256/L streams add the row's partials (fixed assignment and a fixed
+// shared-memory reduction order: deterministic), then sub-warp 0 applies the epilogue.
 template <int L, int V, int MODE>
 __global__ void __launch_bounds__(256) k_spmm_finish(const int4* __restrict__ split_rows, int num_split,
                                                      const float* __restrict__ partials, EpiArgs args) {
-  constexpr int RPW = 32 / L;
   constexpr int LD = 4 * L * V;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane / L, sl = lane % L;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t i = warp * RPW + sub;
-  if (i >= num_split) return;
-  const int4 r = split_rows[i];
+  constexpr int NSUB = 256 / L;
+  __shared__ float4 s_red[NSUB][L * V];
+  const int4 r = split_rows[blockIdx.x];
+  const int sw = threadIdx.x / L, sl = threadIdx.x % L;
   float4 acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < r.z; ++k) {
+#pragma unroll 4
+  for (int k = sw; k < r.z; k += NSUB) {
     const float* pr = partials + (size_t)(r.y + k) * LD + 4 * sl;
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], ld_f4(pr + 4 * L * v));
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) s_red[sw][sl + L * v] = acc[v];
+  __syncthreads();
+  if (sw != 0) return;
+  const int used = min(NSUB, r.z);
+  for (int k = 1; k < used; ++k) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = add4(acc[v], s_red[k][sl + L * v]);
   }
   const size_t off = (size_t)r.x * LD + 4 * sl;
 #pragma unroll
@@ -207,10 +289,9 @@ __global__ void __launch_bounds__(256) k_spmm_finish(const int4* __restrict__ sp
 
 template <int L, int V, int MODE>
 int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
-  constexpr int RPW = 32 / L;
   const int threads = 256, wpb = threads / 32;
   const int64_t n = g->num_nodes;
-  const int grid_light = (int)ceil_div(ceil_div(n, RPW), wpb);
+  const int grid_light = (int)ceil_div(n, (256 / L) * kLightRowsPerSub);
   {
     ProfScope ps(PROF_LIGHT + MODE, st);
     k_spmm_light<L, V, MODE><<<grid_light, threads, 0, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
@@ -227,7 +308,7 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
     LGC_LAUNCH_CHECK();
   }
   if (g->num_split_rows > 0) {
-    const int grid_fin = (int)ceil_div(ceil_div(g->num_split_rows, RPW), wpb);
+    const int grid_fin = (int)g->num_split_rows;
     {
       ProfScope ps(PROF_FINISH + MODE, st);
       k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, st>>>(g->split_rows, (int)g->num_split_rows,
