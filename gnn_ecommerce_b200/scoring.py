@@ -58,6 +58,17 @@ def as_seen_lists(interactions_t, n_rows: int, n_items: int, device) -> SeenList
     return SeenLists(ptr.to(device), cols[order].to(device=device, dtype=torch.int64).contiguous())
 
 
+def _aligned_rows(t: Tensor, d: int) -> Tensor:
+    """Rows must start on 16-byte boundaries (128-bit loads); re-pitch a table that does not
+    (e.g. a contiguous [N, 90] tensor) into a zero-padded [N, ld] copy."""
+    if t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    ld = (d + 3) // 4 * 4
+    out = torch.zeros(t.size(0), ld, dtype=torch.float32, device=t.device)
+    out[:, :d] = t[:, :d]
+    return out
+
+
 def score_topk(user_emb: Tensor, item_emb: Tensor, user_ids: Optional[Tensor],
                seen_ptr: Optional[Tensor], seen_items: Optional[Tensor], k: int,
                d: Optional[int] = None, return_stats: bool = False):
@@ -68,6 +79,7 @@ def score_topk(user_emb: Tensor, item_emb: Tensor, user_ids: Optional[Tensor],
         if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
             raise ValueError(f"{name} must be a 2-D float32 CUDA row table (no CPU fallback)")
     d = int(d if d is not None else min(user_emb.size(1), item_emb.size(1)))
+    user_emb, item_emb = _aligned_rows(user_emb, d), _aligned_rows(item_emb, d)
     n_items = item_emb.size(0)
     if user_ids is None:
         n_users = user_emb.size(0)
