@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--only-scoring", action="store_true", help="skip the training-step timing (dev aid)")
     ap.add_argument("--score-users", type=int, default=0, help="0 = all users (c4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -258,6 +259,9 @@ def main():
     model = model.to(dev)
     trainer = FusedBPRTrainer(model, lr=LR)
     graph = model.graph(ei, ew)
+    if args.only_scoring:
+        print(json.dumps({"scoring": bench_scoring(model, ei, ew, g, dev, args, pk)}), flush=True)
+        return 0
     dev_triples = [tuple(torch.from_numpy(x).to(dev) for x in t) for t in triples]
     pin_triples = [tuple(torch.from_numpy(x).pin_memory() for x in t) for t in triples]
 
@@ -392,7 +396,7 @@ def main():
 
 def bench_scoring(model, ei, ew, g, dev, args, pk):
     import torch
-    from gnn_ecommerce_b200 import ops, scoring, synth
+    from gnn_ecommerce_b200 import _capi, ops, scoring, synth
     k = 20
     with torch.no_grad():
         emb = model.get_embedding(ei, ew)
@@ -411,20 +415,37 @@ def bench_scoring(model, ei, ew, g, dev, args, pk):
     torch.cuda.synchronize()
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
-    beg.record()
+    rep_ms = []
     for _ in range(reps):
+        beg.record()
         top, sc, stats = run()
-    end.record()
+        end.record()
+        torch.cuda.synchronize()
+        rep_ms.append(beg.elapsed_time(end))
+    ms = float(np.median(rep_ms))
+    n_tags = 24
+    ms_arr, cnt_arr = (C.c_double * n_tags)(), (C.c_longlong * n_tags)()
+    lib = _capi.lib()
+    lib.lgc_profile_enable(1)
+    run()
     torch.cuda.synchronize()
-    ms = beg.elapsed_time(end) / reps
+    lib.lgc_profile_read(ms_arr, cnt_arr, n_tags)
+    lib.lgc_profile_enable(0)
+    names = {16: "convert", 17: "gemm", 18: "threshold", 22: "scan", 19: "rescore", 20: "select",
+             21: "exhaustive"}
+    class_ms = {names[t]: ms_arr[t] for t in names}
+    gemm_ms = max(ms_arr[17], 1e-9)
     flops = 2.0 * n_score * g.n_items * model.embedding_dim
     tf = flops / (ms * 1e-3) / 1e12
     st = stats.cpu().tolist()
     return {"metric": "top20_users_per_s", "value": n_score / (ms * 1e-3), "unit": "users/s",
             "users": n_score, "items": g.n_items, "k": k, "ms": ms,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"],
-                         "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
-                         "peak_source": pk["source"]},
+            "roofline": {"bound": "tensor", "kernel": "k_score_gemm", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
+                         "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": flops / (gemm_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                         "peak_source": pk["source"], "kernel_ms": gemm_ms,
+                         "whole_call_tflops": tf, "whole_call_frac": tf / pk["bf16_tflops"]},
+            "class_ms": class_ms, "rep_ms": rep_ms,
             "fallback_users": st[0], "candidate_groups": st[1]}
 
 

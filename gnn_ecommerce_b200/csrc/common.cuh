@@ -48,6 +48,9 @@ enum ProfTag : int {
   PROF_SCORE_GEMM = 17,
   PROF_SCORE_SELECT = 18,
   PROF_SCORE_RESCORE = 19,
+  PROF_SCORE_FINAL = 20,
+  PROF_SCORE_EXHAUSTIVE = 21,
+  PROF_SCORE_SCAN = 22,
   PROF_NUM_TAGS = 24
 };
 bool prof_enabled();

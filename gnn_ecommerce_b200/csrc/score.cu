@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -140,24 +141,36 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns: thread i gets row (lane base + i)
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+#define LGC_R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define LGC_RW8(v, o) "+r"(v[o]), "+r"(v[o + 1]), "+r"(v[o + 2]), "+r"(v[o + 3]), "+r"(v[o + 4]), "+r"(v[o + 5]), "+r"(v[o + 6]), "+r"(v[o + 7])
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : LGC_R8(v, 0), LGC_R8(v, 8), LGC_R8(v, 16), LGC_R8(v, 24)
       : "r"(taddr)
       : "memory");
 }
-// wait for this thread's outstanding tcgen05.ld; the registers are threaded through so the
-// compiler cannot read them before the wait
-__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[16]) {
+// wait for the outstanding tcgen05.ld of two 32-column chunks (registers threaded through)
+__device__ __forceinline__ void tc_wait_ld64(uint32_t (&a)[32], uint32_t (&b)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
-                 "+r"(v[15])
+               : LGC_RW8(a, 0), LGC_RW8(a, 8), LGC_RW8(a, 16), LGC_RW8(a, 24), LGC_RW8(b, 0), LGC_RW8(b, 8),
+                 LGC_RW8(b, 16), LGC_RW8(b, 24)
                :
                : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
@@ -181,29 +194,79 @@ constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0
                             ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // ------------------------------------------------------------------------------------ GEMM + group max
-// gmax16 : [n_tiles*4][u_pad] uint32 = two fp16 group maxima (groups 2p, 2p+1 of the tile)
-// gmax128: [n_tiles][u_pad] fp16 tile maximum
+// 16 words of this thread's TMEM lane, columns taddr.. (registers -> TMEM)
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T: A rows live in TMEM lanes, two fp16 per 32-bit column
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// maximum of 16 consecutive scores v[o..o+15]; columns at or beyond n_valid are masked out
+__device__ __forceinline__ float group_max16(const uint32_t* v, int n_valid) {
+  float f[16];
+#pragma unroll
+  for (int x = 0; x < 16; ++x) f[x] = __uint_as_float(v[x]);
+  if (n_valid < 16) {
+#pragma unroll
+    for (int x = 0; x < 16; ++x)
+      if (x >= n_valid) f[x] = -INFINITY;
+  }
+  const float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]), m2 = max3(f[6], f[7], f[8]);
+  const float m3 = max3(f[9], f[10], f[11]), m4 = max3(f[12], f[13], f[14]);
+  return fmaxf(max3(m0, m1, f[15]), max3(m2, m3, m4));
+}
+
+// Persistent, one CTA per SM. Per step: 256 users (two M=128 halves) x 128 items, K = kp.
+// TMEM (512 columns): a ring of three 128-column fp32 accumulators (one half-tile each) at columns
+// 0/128/256, and -- TS mode -- the users' fp16 rows as the A operand at columns 384.. (kp/2 columns
+// per half). With A in TMEM the tensor core streams only B from shared memory: an SS-mode M=128 x
+// N=128 step needs A + B = 128 B/clk of shared-memory reads and measured 58 % of peak on its own.
+// SS mode (A tiles in shared memory via TMA) remains for kp > 128, where A does not fit in TMEM.
+// Epilogue (8 warps, thread = user row): tcgen05.ld 16 columns at a time, maximum of each group of
+// 16 items; stored per group as an UPPER bound fp16((max + e) * out_scale) rounded up, and per tile
+// as a LOWER bound fp16((max - e) * out_scale) rounded down, e = eps_rel*|a_u|*max|b_tile| + eps_abs.
+//   gmax16 : [n_tiles*4][u_pad] uint32 = upper bounds of groups 2p (low half) and 2p+1 of a tile
+//   gtile  : [n_tiles][u_pad] uint32 = fp16 lower bound (low half) and upper bound (high half) of
+//            the tile maximum
+template <bool TS, int KATOMS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_score_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-             int n_blocks, int n_tiles, int n_items, int katoms, int n_stages, int u_pad, float out_scale,
-             uint32_t* __restrict__ gmax16, __half* __restrict__ gmax128) {
+             const __half* __restrict__ a16, const float* __restrict__ anorm, const float* __restrict__ btile,
+             int n_blocks, int n_tiles, int n_items, int n_stages, int u_pad, float out_scale,
+             float eps_abs, uint32_t* __restrict__ gmax16, uint32_t* __restrict__ gtile, int dbg_mode) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t tile_bytes = 16384u * katoms;                 // one 128-row operand tile
-  uint8_t* smem_a = smem;                                      // 2 tiles
-  uint8_t* smem_b = smem + 2 * tile_bytes;                     // n_stages tiles
+  constexpr int katoms = KATOMS;
+  constexpr uint32_t tile_bytes = 16384u * KATOMS;             // one 128-row operand tile
+  uint8_t* smem_a = smem;                                      // SS: 2 tiles; TS: none
+  uint8_t* smem_b = smem + (TS ? 0 : 2) * tile_bytes;          // n_stages tiles
   uint64_t* bars = (uint64_t*)(smem_b + (size_t)n_stages * tile_bytes);
-  // barrier slots: 0 a_full, 1 a_empty, 2..3 t_full, 4..5 t_empty, 6.. b_full[s], b_empty[s]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 6 + 2 * 8);
+  // barrier slots: 0 a_full, 1 a_empty, 2..4 acc_full, 5..7 acc_empty, 8+s b_full, 16+s b_empty
+  uint32_t* tmem_slot = (uint32_t*)(bars + 24);
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kp = KATOMS * 64;
+  const uint32_t a_col0 = 384u;                                // TS: A of half h at a_col0 + h * kp/2
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(0), 1); mbar_init(bar(1), 1);
-    mbar_init(bar(2), 1); mbar_init(bar(3), 1);
-    mbar_init(bar(4), 8); mbar_init(bar(5), 8);
-    for (int s = 0; s < n_stages; ++s) { mbar_init(bar(6 + s), 1); mbar_init(bar(6 + 8 + s), 1); }
+    mbar_init(bar(0), TS ? 8 : 1); mbar_init(bar(1), 1);
+    for (int b = 0; b < 3; ++b) { mbar_init(bar(2 + b), 1); mbar_init(bar(5 + b), 4); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(bar(8 + s), 1); mbar_init(bar(16 + s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -222,100 +285,147 @@ k_score_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (lane == 0) {
       int s = 0; uint32_t ph = 0, pa = 0;
       for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        mbar_wait(bar(1), pa ^ 1);
-        mbar_expect_tx(bar(0), 2 * tile_bytes);
-        for (int h = 0; h < 2; ++h)
-          for (int ka = 0; ka < katoms; ++ka)
-            tma_load_2d(smem_u32(smem_a + h * tile_bytes + ka * 16384), &map_a, ka * 64,
-                        blk * kUserBlock + h * 128, bar(0));
-        pa ^= 1;
+        if (!TS) {
+          mbar_wait(bar(1), pa ^ 1);
+          mbar_expect_tx(bar(0), 2 * tile_bytes);
+          for (int h = 0; h < 2; ++h)
+            for (int ka = 0; ka < katoms; ++ka)
+              tma_load_2d(smem_u32(smem_a + h * tile_bytes + ka * 16384), &map_a, ka * 64,
+                          blk * kUserBlock + h * 128, bar(0));
+          pa ^= 1;
+        }
         for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(bar(6 + 8 + s), ph ^ 1);
-          mbar_expect_tx(bar(6 + s), tile_bytes);
+          mbar_wait(bar(16 + s), ph ^ 1);
+          mbar_expect_tx(bar(8 + s), tile_bytes);
           for (int ka = 0; ka < katoms; ++ka)
             tma_load_2d(smem_u32(smem_b + (size_t)s * tile_bytes + ka * 16384), &map_b, ka * 64, t * kTileN,
-                        bar(6 + s));
+                        bar(8 + s));
           if (++s == n_stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0) {
-      int s = 0, as = 0; uint32_t ph = 0, pa = 0, pt = 0;
-      const int ksteps = katoms * 4;
-      for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        mbar_wait(bar(0), pa);
-        pa ^= 1;
-        for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(bar(6 + s), ph);
-          mbar_wait(bar(4 + as), pt ^ 1);
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow so every address stays
+    // in uniform registers; one elected lane issues. Descriptors are base + compile-time offsets.
+    int s = 0, buf = 0; uint32_t ph = 0, pa = 0, pb = 0;
+    constexpr int ksteps = KATOMS * 4;
+    const uint64_t b_desc0 = umma_desc(smem_u32(smem_b));
+    const uint64_t a_desc0 = umma_desc(smem_u32(smem_a));
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+      mbar_wait(bar(0), pa);
+      pa ^= 1;
+      tc_fence_after();
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(bar(8 + s), ph);
+        const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)s * (tile_bytes >> 4));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar(5 + buf), pb ^ 1);
           tc_fence_after();
-          const uint32_t b_base = smem_u32(smem_b + (size_t)s * tile_bytes);
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t a_base = smem_u32(smem_a + h * tile_bytes);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + h * 128);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+          if (elect_one_sync()) {
+#pragma unroll
             for (int j = 0; j < ksteps; ++j) {
-              const uint32_t koff = (uint32_t)(j >> 2) * 16384u + (uint32_t)(j & 3) * 32u;
-              tc_mma_f16(d_tmem, umma_desc(a_base + koff), umma_desc(b_base + koff), kIdesc, j > 0);
+              constexpr uint32_t kAtom16 = 16384u >> 4, kStep16 = 32u >> 4;
+              const uint32_t koff16 = (uint32_t)(j >> 2) * kAtom16 + (uint32_t)(j & 3) * kStep16;
+              if (TS)
+                tc_mma_f16_ts(d_tmem, tmem_base + a_col0 + (uint32_t)(h * (kp >> 1) + 8 * j), b_desc + koff16,
+                              kIdesc, j > 0);
+              else
+                tc_mma_f16(d_tmem, a_desc0 + (uint64_t)(h * (tile_bytes >> 4)) + koff16, b_desc + koff16, kIdesc,
+                           j > 0);
             }
+            tc_commit(bar(2 + buf));         // this half-tile's accumulators are ready
+            if (h == 1) tc_commit(bar(16 + s));   // B stage free once these MMAs have read it
           }
-          tc_commit(bar(6 + 8 + s));       // B stage free once these MMAs have read it
-          tc_commit(bar(2 + as));          // accumulators ready for the epilogue
-          if (++s == n_stages) { s = 0; ph ^= 1; }
-          if (++as == 2) { as = 0; pt ^= 1; }
+          __syncwarp();
+          if (++buf == 3) { buf = 0; pb ^= 1; }
         }
-        tc_commit(bar(1));                 // A tile free for the next user block
+        if (++s == n_stages) { s = 0; ph ^= 1; }
       }
+      if (elect_one_sync()) tc_commit(bar(1));   // A free for the next user block
+      __syncwarp();
     }
   } else {
-    // ===== epilogue: warp w may touch TMEM lanes 32*(w%4)..+31
+    // ===== epilogue: warp w may touch TMEM lanes 32*(w%4)..+31; warps 2-5 half 0, 6-9 half 1
     const int q = warp & 3, h = (warp - 2) >> 2;
-    int as = 0; uint32_t pt = 0;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t i = (uint32_t)h, pa = 0;          // half-tile counter of this half: 2 * tiles + h
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
       const int user = blk * kUserBlock + h * 128 + q * 32 + lane;   // < u_pad by construction
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(bar(2 + as), pt);
+      if (TS) {
+        // this thread's fp16 row -> TMEM (A operand): column c holds elements 2c, 2c+1
+        mbar_wait(bar(1), pa ^ 1);             // MMAs of the previous block no longer read A
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + h * 128);
+        const uint4* src = reinterpret_cast<const uint4*>(a16 + (size_t)user * kp);
+        for (int c = 0; c < (kp >> 5); ++c) {
+          uint32_t w[16];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const uint4 v = __ldg(src + 4 * c + x);
+            w[4 * x] = v.x; w[4 * x + 1] = v.y; w[4 * x + 2] = v.z; w[4 * x + 3] = v.w;
+          }
+          tc_st16(tmem_base + lane_base + a_col0 + (uint32_t)(h * (kp >> 1) + 16 * c), w);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(0));
+        pa ^= 1;
+      }
+      const float an = anorm[user] * kEpsRel;
+      for (int t = 0; t < n_tiles; ++t, i += 2) {
+        const uint32_t buf = i % 3u, par = (i / 3u) & 1u;
+        mbar_wait(bar(2 + buf), par);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_base + buf * 128u;
         const int item0 = t * kTileN;
         const bool ragged = item0 + kTileN > n_items;
         float gm[8];
-        uint32_t va[16], vb[16];
-        tc_ld16(taddr, va);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t (&cur)[16] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[16] = (c & 1) ? va : vb;
-          tc_wait_ld(cur);
-          if (c < 7) tc_ld16(taddr + 16 * (c + 1), nxt);
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(cur[i]);
-          if (ragged) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (item0 + c * 16 + i >= n_items) f[i] = -INFINITY;
-          }
-          const float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]), m2 = max3(f[6], f[7], f[8]);
-          const float m3 = max3(f[9], f[10], f[11]), m4 = max3(f[12], f[13], f[14]);
-          gm[c] = fmaxf(max3(m0, m1, f[15]), max3(m2, m3, m4));
+        if (dbg_mode == 1) {                 // timing experiment: MMA/TMA pipeline alone
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(5 + buf));
+          continue;
         }
-        // all TMEM reads of this stage are complete: hand it back to the MMA warp
+        // 128 columns as four 32-column loads, two in flight per wait: the second pair is
+        // requested before the first is reduced, so TMEM latency overlaps the FMNMX work
+        uint32_t va[32], vb[32], vc[32], vd[32];
+        tc_ld32(taddr, va);
+        tc_ld32(taddr + 32, vb);
+        const float e = fmaf(an, __ldg(btile + t), eps_abs);
+        const int nv = ragged ? n_items - item0 : kTileN;     // valid columns of this tile
+        tc_wait_ld64(va, vb);
+        tc_ld32(taddr + 64, vc);
+        tc_ld32(taddr + 96, vd);
+        gm[0] = group_max16(va, nv);
+        gm[1] = group_max16(va + 16, nv - 16);
+        gm[2] = group_max16(vb, nv - 32);
+        gm[3] = group_max16(vb + 16, nv - 48);
+        tc_wait_ld64(vc, vd);
+        // all TMEM reads of this buffer are complete: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(4 + as));
-        if (++as == 2) { as = 0; pt ^= 1; }
+        if (lane == 0) mbar_arrive(bar(5 + buf));
+        gm[4] = group_max16(vc, nv - 64);
+        gm[5] = group_max16(vc + 16, nv - 80);
+        gm[6] = group_max16(vd, nv - 96);
+        gm[7] = group_max16(vd + 16, nv - 112);
 
         const float tm = fmaxf(max3(gm[0], gm[1], gm[2]), max3(max3(gm[3], gm[4], gm[5]), gm[6], gm[7]));
+        if (dbg_mode == 2 && tm != 12345.678f) continue;   // timing experiment: no stores
         uint32_t* g16 = gmax16 + (size_t)(t * 4) * u_pad + user;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const __half2 hh = __floats2half2_rn(gm[2 * p] * out_scale, gm[2 * p + 1] * out_scale);
+          const __half2 hh = __halves2half2(__float2half_ru((gm[2 * p] + e) * out_scale),
+                                            __float2half_ru((gm[2 * p + 1] + e) * out_scale));
           __stcs(g16 + (size_t)p * u_pad, *reinterpret_cast<const uint32_t*>(&hh));
         }
-        gmax128[(size_t)t * u_pad + user] = __float2half_rn(tm * out_scale);
+        {
+          const __half2 hh = __halves2half2(__float2half_rd((tm - e) * out_scale),
+                                            __float2half_ru((tm + e) * out_scale));
+          gtile[(size_t)t * u_pad + user] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
       }
     }
   }
@@ -327,6 +437,16 @@ k_score_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
 }
 
+// max over the 128 item rows of a tile of their (scaled) norms
+__global__ void k_tile_norm(const float* __restrict__ bnorm_item, int n_tiles, float* __restrict__ btile) {
+  const int t = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (t >= n_tiles) return;
+  float m = 0.f;
+  for (int r = lane; r < kTileN; r += 32) m = fmaxf(m, bnorm_item[(size_t)t * kTileN + r]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) btile[t] = m;
+}
+
 // ------------------------------------------------------------------------------------ threshold
 __device__ __forceinline__ unsigned key_of(unsigned short bits) {   // monotone fp16 -> uint16
   return (bits & 0x8000u) ? (unsigned)(~bits & 0xFFFFu) : (unsigned)(bits | 0x8000u);
@@ -335,35 +455,43 @@ __device__ __forceinline__ unsigned short bits_of(unsigned key) {
   return (unsigned short)((key & 0x8000u) ? (key & 0x7FFFu) : (~key & 0xFFFFu));
 }
 
-// CTA = 32 users; their tile maxima are staged in shared memory [n_tiles][32]; each warp then
-// selects, for 4 users, the r-th largest (r = k + n_seen) by bisection on the 16 key bits.
+// CTA = 32 users; the lower bounds of their tile maxima are staged in shared memory as monotone
+// 16-bit keys, one row per user (row pitch = odd number of words: conflict-free both ways); each
+// warp then selects, for 4 users, the r-th largest (r = k + n_seen) by bisection on the key bits,
+// two keys per 32-bit word. T'_u = that value: at least r tiles hold an item whose true score is
+// >= T'_u, at most n_seen of them through a seen item, so the k-th best MASKED score is >= T'_u.
+// Small item sets (few tiles) select among the 16-item groups instead: their stored upper bounds
+// are turned back into lower bounds (U - 2^-10 |U| - 2 e).
 __global__ void __launch_bounds__(256)
-k_threshold(const __half* __restrict__ gmax128, const uint32_t* __restrict__ gmax16, int use_groups, int n_tiles,
-            int u_pad, int n_users, int64_t user0, int k,
-            const int64_t* __restrict__ seen_ptr, const float* __restrict__ anorm,
-            ScoreScalars* sc, int kp, float out_scale, float* __restrict__ thr_grp,
-            float* __restrict__ thr_exact, uint8_t* __restrict__ flag, int32_t* __restrict__ fb_users) {
-  extern __shared__ unsigned short s_keys[];   // [n_sel][32]
+k_threshold(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, int use_groups, int n_tiles,
+            int pitch, int u_pad, int n_users, int64_t user0, int k, const int64_t* __restrict__ seen_ptr,
+            const float* __restrict__ anorm, const float* __restrict__ btile, ScoreScalars* sc, float out_scale,
+            float eps_abs, float* __restrict__ thr_grp, float* __restrict__ thr_exact, uint8_t* __restrict__ flag,
+            int32_t* __restrict__ fb_users) {
+  extern __shared__ unsigned short s_keys[];   // [32][pitch]
   const int u0 = blockIdx.x * 32;
-  // few tiles (small item sets): select among the 16-item group maxima instead -- the same bound
   const int n_sel = use_groups ? n_tiles * 8 : n_tiles;
-  if (use_groups) {
-    for (int i = threadIdx.x; i < n_sel * 32; i += 256) {
-      const int t = i >> 5, j = i & 31;
-      const uint32_t w = gmax16[(size_t)(t >> 1) * u_pad + u0 + j];
-      s_keys[i] = (unsigned short)key_of((unsigned short)((t & 1) ? (w >> 16) : (w & 0xFFFFu)));
+  for (int i = threadIdx.x; i < pitch * 32; i += 256) {
+    const int t = i >> 5, j = i & 31;
+    unsigned short key = 0;                    // padding: below every real key
+    if (t < n_sel) {
+      if (use_groups) {
+        const uint32_t w = gmax16[(size_t)(t >> 1) * u_pad + u0 + j];
+        const float up = __half2float(__ushort_as_half((unsigned short)((t & 1) ? (w >> 16) : (w & 0xFFFFu))));
+        const float e = fmaf(anorm[u0 + j] * kEpsRel, btile[t >> 3], eps_abs) * out_scale;
+        const float lo = up - 0.0009765625f * fabsf(up) - 2.f * e;
+        key = (unsigned short)key_of(__half_as_ushort(__float2half_rd(lo)));
+      } else {
+        key = (unsigned short)key_of((unsigned short)(gtile[(size_t)t * u_pad + u0 + j] & 0xFFFFu));
+      }
+      if (key == 0) key = 1;
     }
-  } else {
-    const unsigned short* src = reinterpret_cast<const unsigned short*>(gmax128);
-    for (int i = threadIdx.x; i < n_sel * 32; i += 256) {
-      const int t = i >> 5, j = i & 31;
-      s_keys[i] = (unsigned short)key_of(src[(size_t)t * u_pad + u0 + j]);
-    }
+    s_keys[j * pitch + t] = key;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ea = scale_exp(sc->amax_bits), eb = scale_exp(sc->bmax_bits);
-  const float bnorm = __uint_as_float(sc->bnorm_bits);
+  const int n_words = pitch >> 1;
   for (int j = warp; j < 32; j += 8) {
     const int u = u0 + j;
     if (u >= n_users) break;
@@ -378,132 +506,231 @@ k_threshold(const __half* __restrict__ gmax128, const uint32_t* __restrict__ gma
       }
       continue;
     }
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(s_keys + j * pitch);
     unsigned prefix = 0;
     for (int bit = 15; bit >= 0; --bit) {
       const unsigned cand = prefix | (1u << bit);
+      const unsigned cand2 = cand | (cand << 16);
       int cnt = 0;
-      for (int t = lane; t < n_sel; t += 32) cnt += (s_keys[t * 32 + j] >= cand) ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      for (int w = lane; w < n_words; w += 32) cnt += __popc(__vcmpgeu2(row[w], cand2));
+      cnt = __reduce_add_sync(0xffffffffu, cnt) >> 4;
       if (cnt >= r) prefix = cand;
     }
     if (lane == 0) {
-      const float T = __half2float(__ushort_as_half(bits_of(prefix)));      // stored units
-      const float eps = (kEpsRel * anorm[u] * bnorm + (float)kp * 0.001953125f) * out_scale;
+      const float T = __half2float(__ushort_as_half(bits_of(prefix)));      // stored units, lower bound
       flag[u] = 0;
-      thr_grp[u] = T - 2.f * eps;
+      thr_grp[u] = T;
       // back to true units: stored = score * 2^(ea+eb) * out_scale
-      thr_exact[u] = scalbnf((T - eps) / out_scale, -(ea + eb));
+      thr_exact[u] = scalbnf(T / out_scale, -(ea + eb));
     }
   }
 }
 
 // ------------------------------------------------------------------------------------ exact re-scoring
 // Fixed summation order shared by the fast path and the exhaustive path (identical scores):
-// half `hf` takes the float4 chunks hf, hf+2, ...; the total is half0 + half1.
-__device__ __forceinline__ float dot_half(const float4* __restrict__ a, const float4* __restrict__ b, int d4, int hf) {
-  float s = 0.f;
-  for (int c = hf; c < d4; c += 2) {
-    const float4 x = a[c], y = b[c];
-    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+// even float4 chunks into one accumulator, odd chunks into another, total = even + odd.
+__device__ __forceinline__ float dot_exact(const float4* __restrict__ a, const float4* __restrict__ b, int d4) {
+  float s0 = 0.f, s1 = 0.f;
+  int c = 0;
+  for (; c + 1 < d4; c += 2) {
+    const float4 x0 = a[c], y0 = b[c], x1 = a[c + 1], y1 = b[c + 1];
+    s0 = fmaf(x0.x, y0.x, s0); s0 = fmaf(x0.y, y0.y, s0); s0 = fmaf(x0.z, y0.z, s0); s0 = fmaf(x0.w, y0.w, s0);
+    s1 = fmaf(x1.x, y1.x, s1); s1 = fmaf(x1.y, y1.y, s1); s1 = fmaf(x1.z, y1.z, s1); s1 = fmaf(x1.w, y1.w, s1);
   }
-  return s;
+  if (c < d4) {
+    const float4 x0 = a[c], y0 = b[c];
+    s0 = fmaf(x0.x, y0.x, s0); s0 = fmaf(x0.y, y0.y, s0); s0 = fmaf(x0.z, y0.z, s0); s0 = fmaf(x0.w, y0.w, s0);
+  }
+  return s0 + s1;
+}
+__device__ __forceinline__ float4 load_row_f4(const float* __restrict__ row, int c, int d) {
+  if (4 * c + 3 < d) return __ldg(reinterpret_cast<const float4*>(row + 4 * c));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (4 * c < d) v.x = row[4 * c];
+  if (4 * c + 1 < d) v.y = row[4 * c + 1];
+  if (4 * c + 2 < d) v.z = row[4 * c + 2];
+  return v;
 }
 
-constexpr int kRescoreBatch = 1024;   // users scanned per CTA iteration
+constexpr int kRowsPerWarp = 16;      // user rows a warp keeps in flight
 
-// grid (n_tiles, user splits). The CTA keeps its 128 item rows (fp32) in shared memory, scans the
-// stored group maxima of its users against their thresholds, and re-scores the hits exactly.
+// Candidate (user, group) pairs bucketed by item tile, in two streaming passes over the stored
+// bounds: FILL == false counts the hits of every tile, FILL == true writes `(user << 3) | group`
+// into the tile's slice of `list` (slices from the prefix sum of the counts). A tile is looked at
+// in detail (its four group words) only when its own upper bound reaches the user's threshold.
+// Entries that do not fit `list_cap` are dropped and their user is sent to the exhaustive path.
+template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_rescore(const uint32_t* __restrict__ gmax16, int u_pad, int n_users, int64_t user0, int n_items, int d,
-          const float* __restrict__ user_emb, int ld_user, const int64_t* __restrict__ user_ids,
-          const float* __restrict__ item_emb, int ld_item, const float* __restrict__ thr_grp,
-          const float* __restrict__ thr_exact, const int64_t* __restrict__ seen_ptr,
-          const int64_t* __restrict__ seen_items, int* __restrict__ cand_cnt, int32_t* __restrict__ cand_item,
+k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, int u_pad, int n_users,
+       const float* __restrict__ thr_grp, int* __restrict__ tile_cnt, const int* __restrict__ tile_off,
+       int* __restrict__ tile_cur, int* __restrict__ list, int list_cap, uint8_t* __restrict__ flag) {
+  const int tile = blockIdx.x;
+  const int per = (n_users + gridDim.y - 1) / gridDim.y;
+  const int u_beg = blockIdx.y * per, u_end = min(n_users, u_beg + per);
+  const int lane = threadIdx.x & 31;
+  int my = 0;
+  for (int u0 = u_beg; u0 < u_end; u0 += 256) {
+    const int u = u0 + threadIdx.x;
+    unsigned hits = 0;
+    if (u < u_end) {
+      const float thr = thr_grp[u];
+      const uint32_t tw = __ldcs(gtile + (size_t)tile * u_pad + u);
+      const float up = __half2float(__ushort_as_half((unsigned short)(tw >> 16)));
+      if (up >= thr) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const uint32_t w = __ldcs(gmax16 + (size_t)(tile * 4 + p) * u_pad + u);
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+          if (f.x >= thr) hits |= 1u << (2 * p);
+          if (f.y >= thr) hits |= 1u << (2 * p + 1);
+        }
+      }
+    }
+    const int c = __popc(hits);
+    if (!FILL) {
+      my += c;
+    } else {
+      int incl = c;                                   // warp-aggregated slot allocation
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&tile_cur[tile], total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = tile_off[tile] + base + incl - c;
+        while (hits) {
+          const int g = __ffs(hits) - 1;
+          hits &= hits - 1;
+          if (pos < list_cap) list[pos] = (u << 3) | g;
+          else flag[u] = 2;                            // picked up by k_select -> exhaustive path
+          ++pos;
+        }
+      }
+    }
+  }
+  if (!FILL) {
+    my = __reduce_add_sync(0xffffffffu, my);
+    if (lane == 0 && my) atomicAdd(&tile_cnt[tile], my);
+  }
+}
+
+// exclusive prefix sum of the per-tile counts (n_tiles is a few hundred to a few thousand)
+__global__ void k_tile_prefix(const int* __restrict__ tile_cnt, int n_tiles, int* __restrict__ tile_off,
+                              ScoreScalars* __restrict__ sc) {
+  __shared__ long long s_part[256];
+  const int per = (n_tiles + 255) / 256;
+  const int b = threadIdx.x * per, e = min(n_tiles, b + per);
+  long long sum = 0;
+  for (int t = b; t < e; ++t) sum += tile_cnt[t];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int i = 0; i < 256; ++i) { const long long v = s_part[i]; s_part[i] = run; run += v; }
+    sc->n_groups += (unsigned long long)run;
+  }
+  __syncthreads();
+  long long run = s_part[threadIdx.x];
+  for (int t = b; t < e; ++t) {
+    tile_off[t] = (int)min(run, (long long)0x7fffffff);
+    run += tile_cnt[t];
+  }
+  if (threadIdx.x == 255) tile_off[n_tiles] = (int)min(run, (long long)0x7fffffff);
+}
+
+// grid (n_tiles, splits). The CTA keeps its 128 item rows (fp32) in shared memory and walks its
+// share of the tile's candidate list. Per step a warp takes 16 (user, group) pairs: their
+// metadata, then all 16 user rows, are requested before anything is used -- that is what hides
+// the HBM latency of these random 256-byte reads -- then every lane computes 8 exact fp32 dot
+// products (lane = item of the group, half-warp = 8 of the pairs).
+__global__ void __launch_bounds__(256, 3)
+k_rescore(const int* __restrict__ list, const int* __restrict__ tile_off, int list_cap, int64_t user0, int n_items,
+          int d, const float* __restrict__ user_emb, int ld_user, const int64_t* __restrict__ user_ids,
+          const float* __restrict__ item_emb, int ld_item, const float* __restrict__ thr_exact,
+          const int64_t* __restrict__ seen_ptr, const int64_t* __restrict__ seen_items,
+          const uint8_t* __restrict__ flag, int* __restrict__ cand_cnt, int32_t* __restrict__ cand_item,
           float* __restrict__ cand_score, ScoreScalars* __restrict__ sc) {
   extern __shared__ __align__(16) uint8_t smem_rs[];
   const int d4 = (d + 3) >> 2;
   const int row_f4 = d4 + 1;                          // +16 B per row: conflict-free float4 reads
   float4* s_items = reinterpret_cast<float4*>(smem_rs);                 // [128][row_f4]
-  float4* s_user = s_items + 128 * row_f4;                              // [8 warps][d4]
-  int* s_queue = reinterpret_cast<int*>(s_user + 8 * d4);               // [kRescoreBatch * 8]
-  __shared__ int s_qn;
+  float4* s_rows = s_items + 128 * row_f4;                              // [8 warps][16][d4]
 
   const int tile = blockIdx.x, item0 = tile * kTileN;
+  const int beg = min(tile_off[tile], list_cap), end = min(tile_off[tile + 1], list_cap);
+  if (beg >= end) return;
   for (int i = threadIdx.x; i < 128 * d4; i += 256) {
     const int r = i / d4, c = i % d4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (item0 + r < n_items) {
-      const float* p = item_emb + (size_t)(item0 + r) * ld_item + 4 * c;
-      if (4 * c + 3 < d) v = *reinterpret_cast<const float4*>(p);
-      else { v.x = p[0]; if (4 * c + 1 < d) v.y = p[1]; if (4 * c + 2 < d) v.z = p[2]; }
-    }
+    if (item0 + r < n_items) v = load_row_f4(item_emb + (size_t)(item0 + r) * ld_item, c, d);
     s_items[r * row_f4 + c] = v;
   }
-  const int per_split = round_up((u_pad + gridDim.y - 1) / gridDim.y, kRescoreBatch);
-  const int u_beg = blockIdx.y * per_split, u_end = min(n_users, u_beg + per_split);
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long my_groups = 0, my_emit = 0;
-
-  for (int base = u_beg; base < u_end; base += kRescoreBatch) {
-    if (threadIdx.x == 0) s_qn = 0;
-    __syncthreads();
-    // ---- scan
-#pragma unroll
-    for (int j = 0; j < kRescoreBatch / 256; ++j) {
-      const int u = base + threadIdx.x + 256 * j;
-      if (u < u_end) {
-        const float thr = thr_grp[u];
-        uint32_t w[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) w[p] = __ldcs(gmax16 + (size_t)(tile * 4 + p) * u_pad + u);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[p]));
-          if (f.x >= thr) s_queue[atomicAdd(&s_qn, 1)] = (u << 3) | (2 * p);
-          if (f.y >= thr) s_queue[atomicAdd(&s_qn, 1)] = (u << 3) | (2 * p + 1);
-        }
+  const int it = lane & 15, hw = lane >> 4;
+  float4* rows = s_rows + (size_t)warp * kRowsPerWarp * d4;
+  unsigned long long my_emit = 0;
+  const int step = gridDim.y * 8 * kRowsPerWarp;
+  for (int e0 = beg + (blockIdx.y * 8 + warp) * kRowsPerWarp; e0 < end; e0 += step) {
+    const int ne = min(kRowsPerWarp, end - e0);
+    // lanes 0..15 own one pair each: entry + per-user metadata
+    int ent = 0; int64_t uid = 0, sb = 0; float thr = INFINITY; int n_seen = 0;
+    if (lane < ne) {
+      ent = list[e0 + lane];
+      const int u = ent >> 3;
+      if (flag[u] == 0) {
+        uid = user_ids ? user_ids[user0 + u] : user0 + u;
+        thr = thr_exact[u];
+        if (seen_ptr) { sb = seen_ptr[user0 + u]; n_seen = (int)(seen_ptr[user0 + u + 1] - sb); }
       }
     }
-    __syncthreads();
-    const int qn = s_qn;
-    // ---- exact scores of the hit groups: one warp per (user, group)
-    for (int e = warp; e < qn; e += 8) {
-      const int ent = s_queue[e], u = ent >> 3, g = ent & 7;
-      const int64_t uid = user_ids ? user_ids[user0 + u] : user0 + u;
-      const float* urow = user_emb + (size_t)uid * ld_user;
-      float4* su = s_user + warp * d4;
-      __syncwarp();
-      for (int c = lane; c < d4; c += 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (4 * c + 3 < d) v = *reinterpret_cast<const float4*>(urow + 4 * c);
-        else { v.x = urow[4 * c]; if (4 * c + 1 < d) v.y = urow[4 * c + 1]; if (4 * c + 2 < d) v.z = urow[4 * c + 2]; }
-        su[c] = v;
+    __syncwarp();
+    for (int c0 = 0; c0 < d4; c0 += 16) {             // half-warp hw stages rows hw, hw+2, ...
+      float4 v[kRowsPerWarp / 2];
+      const int c = c0 + it;
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+        const int slot = 2 * i + hw;
+        const int64_t id = __shfl_sync(0xffffffffu, uid, slot);
+        if (slot < ne && c < d4) v[i] = load_row_f4(user_emb + (size_t)id * ld_user, c, d);
       }
-      __syncwarp();
-      const int it = lane & 15, hf = lane >> 4;
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+        const int slot = 2 * i + hw;
+        if (slot < ne && c < d4) rows[slot * d4 + c] = v[i];
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+      const int slot = 2 * i + hw;
+      const int e_ent = __shfl_sync(0xffffffffu, ent, slot);
+      const float e_thr = __shfl_sync(0xffffffffu, thr, slot);
+      const int64_t e_sb = __shfl_sync(0xffffffffu, sb, slot);
+      const int e_ns = __shfl_sync(0xffffffffu, n_seen, slot);
+      if (slot >= ne) continue;
+      const int u = e_ent >> 3, g = e_ent & 7;
       const int local = g * kGroup + it, item = item0 + local;
-      float s = dot_half(su, s_items + local * row_f4, d4, hf);
-      const float other = __shfl_xor_sync(0xffffffffu, s, 16);
-      s = hf == 0 ? s + other : other + s;           // half0 + half1 on every lane
-      if (hf == 0 && item < n_items && s >= thr_exact[u]) {
+      const float sco = dot_exact(rows + slot * d4, s_items + local * row_f4, d4);
+      if (item < n_items && sco >= e_thr) {
         bool seen = false;
-        if (seen_ptr) {
-          for (int64_t q = seen_ptr[user0 + u]; q < seen_ptr[user0 + u + 1]; ++q) seen |= (seen_items[q] == item);
-        }
+        for (int q = 0; q < e_ns; ++q) seen |= (seen_items[e_sb + q] == item);
         if (!seen) {
-          const int slot = atomicAdd(&cand_cnt[u], 1);
-          if (slot < kCap) {
-            cand_item[(size_t)u * kCap + slot] = item;
-            cand_score[(size_t)u * kCap + slot] = s;
+          const int pos = atomicAdd(&cand_cnt[u], 1);
+          if (pos < kCap) {
+            cand_item[(size_t)u * kCap + pos] = item;
+            cand_score[(size_t)u * kCap + pos] = sco + 0.f;      // -0.0 -> +0.0
           }
           ++my_emit;
         }
       }
     }
-    if (threadIdx.x == 0) my_groups += qn;
   }
   if (my_emit) atomicAdd(&sc->n_emitted, my_emit);
-  if (threadIdx.x == 0 && my_groups) atomicAdd(&sc->n_groups, my_groups);
 }
 
 // ------------------------------------------------------------------------------------ final selection
@@ -511,37 +738,92 @@ k_rescore(const uint32_t* __restrict__ gmax16, int u_pad, int n_users, int64_t u
 __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
   return sa > sb || (sa == sb && ia < ib);
 }
+// (score, item) -> 64-bit key whose DEscending order is that total order; 0 = empty slot
+__device__ __forceinline__ unsigned long long sel_key(float s, int item) {
+  const unsigned b = __float_as_uint(s + 0.f);
+  const unsigned ord = b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+  return ((unsigned long long)ord << 32) | (unsigned)(0x7FFFFFFF - item);
+}
+__device__ __forceinline__ float sel_score(unsigned long long key) {
+  const unsigned ord = (unsigned)(key >> 32);
+  return __uint_as_float((ord & 0x80000000u) ? (ord ^ 0x80000000u) : ~ord);
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+  const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
 
 // One warp per user. Entries = exact candidates + the user's seen items with masked score 0.0
-// (reference: pred * (1 - mask), src/lightgcn.py:175). Round r picks the first entry strictly
-// after the previous pick, so duplicates collapse and nothing is mutated.
+// (reference: pred * (1 - mask), src/lightgcn.py:175); rows of seen_items hold distinct ids.
+// Up to 64 entries: bitonic sort across the warp (1 or 2 keys per lane). More (long seen lists):
+// k rounds, each picking the first entry strictly after the previous pick.
 __global__ void __launch_bounds__(256)
-k_select(int n_users, int64_t user0, int n_items, int k, uint8_t* flag, const int* __restrict__ cand_cnt, const int32_t* __restrict__ cand_item,
-         const float* __restrict__ cand_score, const int64_t* __restrict__ seen_ptr,
-         const int64_t* __restrict__ seen_items, int64_t* __restrict__ topk_items,
-         float* __restrict__ topk_scores, int32_t* __restrict__ fb_users, ScoreScalars* __restrict__ sc) {
+k_select(int n_users, int64_t user0, int n_items, int k, uint8_t* flag, const int* __restrict__ cand_cnt,
+         const int32_t* __restrict__ cand_item, const float* __restrict__ cand_score,
+         const int64_t* __restrict__ seen_ptr, const int64_t* __restrict__ seen_items,
+         int64_t* __restrict__ topk_items, float* __restrict__ topk_scores, int32_t* __restrict__ fb_users,
+         ScoreScalars* __restrict__ sc) {
   const int u = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (u >= n_users || flag[u]) return;
+  if (u >= n_users || flag[u] == 1) return;          // 1: already on the exhaustive list
   const int cnt = cand_cnt[u];
-  if (cnt > kCap) {
+  if (cnt > kCap || flag[u] == 2) {                   // 2: candidate entries were dropped
     if (lane == 0) { flag[u] = 1; fb_users[atomicAdd(&sc->fb_count, 1)] = u; }
     return;
   }
   const int64_t sb = seen_ptr ? seen_ptr[user0 + u] : 0, se = seen_ptr ? seen_ptr[user0 + u + 1] : 0;
   const int n_seen = (int)(se - sb), total = cnt + n_seen;
+  if (total <= 64) {
+    auto entry = [&](int e) -> unsigned long long {
+      if (e < cnt) return sel_key(cand_score[(size_t)u * kCap + e], cand_item[(size_t)u * kCap + e]);
+      if (e < total) {
+        const int64_t si = seen_items[sb + (e - cnt)];
+        return (si >= 0 && si < n_items) ? sel_key(0.f, (int)si) : 0ull;
+      }
+      return 0ull;
+    };
+    unsigned long long k0 = entry(lane), k1 = total > 32 ? entry(lane + 32) : 0ull;
+    const int top = total > 32 ? 64 : 32;
+    for (int size = 2; size <= top; size <<= 1) {
+      for (int stride = size >> 1; stride; stride >>= 1) {
+        if (stride == 32) {                       // partner is this lane's other key
+          const unsigned long long hi = max(k0, k1), lo = min(k0, k1);
+          k0 = hi; k1 = lo;
+          continue;
+        }
+        const bool lower = (lane & stride) == 0;
+        {
+          const unsigned long long o = shfl_xor_u64(k0, stride);
+          const bool desc = (lane & size) == 0;     // index x = lane
+          k0 = (lower == desc) ? max(k0, o) : min(k0, o);
+        }
+        if (top == 64) {
+          const unsigned long long o = shfl_xor_u64(k1, stride);
+          const bool desc = ((lane + 32) & size) == 0;   // index x = lane + 32
+          k1 = (lower == desc) ? max(k1, o) : min(k1, o);
+        }
+      }
+    }
+    if (lane < k) {
+      const bool found = k0 != 0ull;
+      topk_items[(size_t)(user0 + u) * k + lane] = found ? (int64_t)(0x7FFFFFFF - (int)(unsigned)k0) : -1;
+      if (topk_scores) topk_scores[(size_t)(user0 + u) * k + lane] = found ? sel_score(k0) : -INFINITY;
+    }
+    return;
+  }
   float ps = INFINITY; int pi = -1;
   for (int r = 0; r < k; ++r) {
     float bs = -INFINITY; int bi = 0x7fffffff;
     for (int e = lane; e < total; e += 32) {
-      float s; int it;
-      if (e < cnt) { s = cand_score[(size_t)u * kCap + e]; it = cand_item[(size_t)u * kCap + e]; }
+      float s; int itm;
+      if (e < cnt) { s = cand_score[(size_t)u * kCap + e]; itm = cand_item[(size_t)u * kCap + e]; }
       else {
         const int64_t si = seen_items[sb + (e - cnt)];
         if (si < 0 || si >= n_items) continue;
-        s = 0.f; it = (int)si;
+        s = 0.f; itm = (int)si;
       }
-      if (before(ps, pi, s, it) && before(s, it, bs, bi)) { bs = s; bi = it; }
+      if (before(ps, pi, s, itm) && before(s, itm, bs, bi)) { bs = s; bi = itm; }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -657,9 +939,9 @@ __global__ void k_add_stats(const ScoreScalars* __restrict__ sc, int64_t* __rest
 
 // ------------------------------------------------------------------------------------ host side
 struct Layout {
-  int kp, katoms, n_stages, n_tiles, i_pad, chunk, chunk_pad;
+  int kp, katoms, n_stages, n_tiles, i_pad, chunk, chunk_pad, ts, list_cap;
   size_t gemm_smem;
-  size_t off_scal, off_b16, off_a16, off_anorm, off_g16, off_g128, off_thr_grp, off_thr_exact, off_flag,
+  size_t off_scal, off_b16, off_bnorm, off_btile, off_a16, off_anorm, off_g16, off_g128, off_tcnt, off_toff, off_tcur, off_list, off_thr_grp, off_thr_exact, off_flag,
       off_fb, off_cnt, off_citem, off_cscore, off_scratch;
   int n_exh_ctas;
   size_t bytes;
@@ -674,15 +956,17 @@ bool make_layout(int64_t n_users, int64_t n_items, int d, int k, Layout* L) {
   L->katoms = L->kp / 64;
   const size_t tile_bytes = 16384u * L->katoms;
   const size_t budget = 200 * 1024;
-  int ns = (int)((budget - 2 * tile_bytes) / tile_bytes);
-  L->n_stages = std::max(1, std::min(ns, 6));
-  L->gemm_smem = 1024 + (2 + (size_t)L->n_stages) * tile_bytes + 256;
+  L->ts = L->kp <= 128 ? 1 : 0;          // A operand in TMEM (fits beside three accumulators)
+  const size_t a_tiles = L->ts ? 0 : 2;
+  int ns = (int)((budget - a_tiles * tile_bytes) / tile_bytes);
+  L->n_stages = std::max(1, std::min(ns, 8));
+  L->gemm_smem = 1024 + (a_tiles + (size_t)L->n_stages) * tile_bytes + 256;
   L->i_pad = round_up(n_items, kTileN);
   L->n_tiles = L->i_pad / kTileN;
   // bytes per user of the chunk-sized buffers
-  const size_t per_user = (size_t)L->kp * 2 + 4 + (size_t)L->n_tiles * 4 * 4 + (size_t)L->n_tiles * 2 + 4 + 4 + 1 +
-                          4 + 4 + (size_t)kCap * 8;
-  const size_t fixed = (size_t)L->i_pad * L->kp * 2 + (size_t)296 * n_items * 4 + (1 << 16);
+  const size_t per_user = (size_t)L->kp * 2 + 4 + (size_t)L->n_tiles * 4 * 4 + (size_t)L->n_tiles * 4 + 4 + 4 + 1 +
+                          4 + 4 + (size_t)kCap * 8 + 40 * 4;
+  const size_t fixed = (size_t)L->i_pad * (L->kp * 2 + 8) + (size_t)296 * n_items * 4 + (1 << 16);
   int64_t chunk = round_up(n_users, kUserBlock);
   if (fixed + per_user * (size_t)chunk > kWorkspaceBudget) {
     int64_t c = (int64_t)((kWorkspaceBudget > fixed ? kWorkspaceBudget - fixed : 0) / per_user);
@@ -698,10 +982,17 @@ bool make_layout(int64_t n_users, int64_t n_items, int d, int k, Layout* L) {
   const size_t cp = (size_t)L->chunk_pad;
   L->off_scal = take(sizeof(ScoreScalars));
   L->off_b16 = take((size_t)L->i_pad * L->kp * 2);
+  L->off_bnorm = take((size_t)L->i_pad * 4);
+  L->off_btile = take((size_t)L->n_tiles * 4);
   L->off_a16 = take(cp * L->kp * 2);
   L->off_anorm = take(cp * 4);
   L->off_g16 = take((size_t)L->n_tiles * 4 * cp * 4);
-  L->off_g128 = take((size_t)L->n_tiles * cp * 2);
+  L->off_g128 = take((size_t)L->n_tiles * cp * 4);
+  L->list_cap = (int)std::min<size_t>((size_t)0x7ffffff0, std::max<size_t>((size_t)1 << 16, cp * 40));
+  L->off_tcnt = take((size_t)(L->n_tiles + 1) * 4);
+  L->off_toff = take((size_t)(L->n_tiles + 1) * 4);
+  L->off_tcur = take((size_t)(L->n_tiles + 1) * 4);
+  L->off_list = take((size_t)L->list_cap * 4);
   L->off_thr_grp = take(cp * 4);
   L->off_thr_exact = take(cp * 4);
   L->off_flag = take(cp);
@@ -762,9 +1053,15 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
   ScoreScalars* sc = (ScoreScalars*)(ws + L.off_scal);
   __half* b16 = (__half*)(ws + L.off_b16);
   __half* a16 = (__half*)(ws + L.off_a16);
+  float* bnorm_item = (float*)(ws + L.off_bnorm);
+  float* btile = (float*)(ws + L.off_btile);
   float* anorm = (float*)(ws + L.off_anorm);
   uint32_t* g16 = (uint32_t*)(ws + L.off_g16);
-  __half* g128 = (__half*)(ws + L.off_g128);
+  uint32_t* g128 = (uint32_t*)(ws + L.off_g128);
+  int* tile_cnt = (int*)(ws + L.off_tcnt);
+  int* tile_off = (int*)(ws + L.off_toff);
+  int* tile_cur = (int*)(ws + L.off_tcur);
+  int* list = (int*)(ws + L.off_list);
   float* thr_grp = (float*)(ws + L.off_thr_grp);
   float* thr_exact = (float*)(ws + L.off_thr_exact);
   uint8_t* flag = ws + L.off_flag;
@@ -780,7 +1077,10 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    LGC_CUDA(cudaFuncSetAttribute(k_score_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     LGC_CUDA(cudaFuncSetAttribute(k_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LGC_CUDA(cudaFuncSetAttribute(k_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
@@ -792,6 +1092,8 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
   rc = encode_map(&map_b, b16, L.kp, L.i_pad);
   if (rc) return rc;
 
+  const char* dbg_env = getenv("LGC_SCORE_DEBUG_MODE");   // timing experiments only (results invalid)
+  const int dbg_mode = dbg_env ? atoi(dbg_env) : 0;
   const int out_e = out_scale_exp(L.kp);
   const float out_scale = ldexpf(1.0f, out_e);
 
@@ -803,19 +1105,25 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     k_absmax<<<kNumSMs * 4, 256, 0, st>>>(a->item_emb, a->ld_item, a->d, nullptr, a->n_items, &sc->bmax_bits);
     LGC_LAUNCH_CHECK();
     k_convert<<<(int)ceil_div((int64_t)L.i_pad * 32, 256), 256, 0, st>>>(
-        a->item_emb, a->ld_item, a->d, nullptr, 0, a->n_items, L.i_pad, L.kp, &sc->bmax_bits, b16, nullptr,
+        a->item_emb, a->ld_item, a->d, nullptr, 0, a->n_items, L.i_pad, L.kp, &sc->bmax_bits, b16, bnorm_item,
         &sc->bnorm_bits);
+    LGC_LAUNCH_CHECK();
+    k_tile_norm<<<(int)ceil_div((int64_t)L.n_tiles * 32, 256), 256, 0, st>>>(bnorm_item, L.n_tiles, btile);
     LGC_LAUNCH_CHECK();
   }
 
   const int use_groups = L.n_tiles < 256 ? 1 : 0;
-  const size_t thr_smem = (size_t)L.n_tiles * (use_groups ? 8 : 1) * 32 * 2;
+  const int n_sel = L.n_tiles * (use_groups ? 8 : 1);
+  int pitch = (n_sel + 1) / 2 * 2;                 // keys per user row: even, with an odd word count
+  if ((pitch / 2) % 2 == 0) pitch += 2;
+  const size_t thr_smem = (size_t)pitch * 32 * 2;
+  const float eps_abs = (float)L.kp * 0.001953125f;   // subnormal fp16 inputs: kp * 2^-9 (scaled units)
   if (thr_smem > 200 * 1024) {
     set_error("lgc_score_topk: n_items above 409600 is not supported yet");
     return LGC_ERR_UNSUPPORTED;
   }
   const int d4 = (a->d + 3) / 4;
-  const size_t rs_smem = (size_t)128 * (d4 + 1) * 16 + (size_t)8 * d4 * 16 + (size_t)kRescoreBatch * 8 * 4;
+  const size_t rs_smem = (size_t)128 * (d4 + 1) * 16 + (size_t)8 * kRowsPerWarp * d4 * 16;
   const size_t ex_smem = (size_t)d4 * 16;
 
   for (int64_t user0 = 0; user0 < a->n_users; user0 += L.chunk) {
@@ -834,29 +1142,59 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     {
       ProfScope ps(PROF_SCORE_GEMM, st);
       const int grid = std::min(n_blocks, kNumSMs);
-      k_score_gemm<<<grid, kGemmThreads, L.gemm_smem, st>>>(map_a, map_b, n_blocks, L.n_tiles, (int)a->n_items,
-                                                           L.katoms, L.n_stages, L.chunk_pad, out_scale, g16, g128);
+#define LGC_GEMM_LAUNCH(TS_, KA_)                                                                          \
+  k_score_gemm<TS_, KA_><<<grid, kGemmThreads, L.gemm_smem, st>>>(                                         \
+      map_a, map_b, a16, anorm, btile, n_blocks, L.n_tiles, (int)a->n_items, L.n_stages, L.chunk_pad,      \
+      out_scale, eps_abs, g16, g128, dbg_mode)
+      if (L.katoms == 1) LGC_GEMM_LAUNCH(true, 1);
+      else if (L.katoms == 2) LGC_GEMM_LAUNCH(true, 2);
+      else if (L.katoms == 3) LGC_GEMM_LAUNCH(false, 3);
+      else LGC_GEMM_LAUNCH(false, 4);
+#undef LGC_GEMM_LAUNCH
+      LGC_LAUNCH_CHECK();
+    }
+    if (dbg_mode) continue;          // timing experiments: GEMM only, outputs are not valid
+    {
+      ProfScope ps(PROF_SCORE_SELECT, st);
+      k_threshold<<<nu_pad / 32, 256, thr_smem, st>>>(g128, g16, use_groups, L.n_tiles, pitch, L.chunk_pad, nu, user0,
+                                                     a->k, a->seen_ptr, anorm, btile, sc, out_scale, eps_abs, thr_grp,
+                                                     thr_exact, flag, fb);
       LGC_LAUNCH_CHECK();
     }
     {
-      ProfScope ps(PROF_SCORE_SELECT, st);
-      k_threshold<<<nu_pad / 32, 256, thr_smem, st>>>(g128, g16, use_groups, L.n_tiles, L.chunk_pad, nu, user0, a->k, a->seen_ptr,
-                                                     anorm, sc, L.kp, out_scale, thr_grp, thr_exact, flag, fb);
+      ProfScope ps(PROF_SCORE_SCAN, st);
+      LGC_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(L.n_tiles + 1) * 4, st));
+      LGC_CUDA(cudaMemsetAsync(tile_cur, 0, (size_t)(L.n_tiles + 1) * 4, st));
+      const int ssplits = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(kNumSMs * 16, L.n_tiles),
+                                                                      ceil_div(nu, 256)));
+      dim3 sgrid(L.n_tiles, ssplits);
+      k_scan<false><<<sgrid, 256, 0, st>>>(g128, g16, L.chunk_pad, nu, thr_grp, tile_cnt, tile_off, tile_cur, list,
+                                          L.list_cap, flag);
+      LGC_LAUNCH_CHECK();
+      k_tile_prefix<<<1, 256, 0, st>>>(tile_cnt, L.n_tiles, tile_off, sc);
+      LGC_LAUNCH_CHECK();
+      k_scan<true><<<sgrid, 256, 0, st>>>(g128, g16, L.chunk_pad, nu, thr_grp, tile_cnt, tile_off, tile_cur, list,
+                                         L.list_cap, flag);
       LGC_LAUNCH_CHECK();
     }
     {
       ProfScope ps(PROF_SCORE_RESCORE, st);
-      int splits = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(kNumSMs * 8, L.n_tiles),
-                                                               ceil_div(nu, kRescoreBatch)));
-      dim3 grid(L.n_tiles, splits);
-      k_rescore<<<grid, 256, rs_smem, st>>>(g16, L.chunk_pad, nu, user0, (int)a->n_items, a->d, a->user_emb,
-                                            a->ld_user, a->user_ids, a->item_emb, a->ld_item, thr_grp, thr_exact,
-                                            a->seen_ptr, a->seen_items, cnt, citem, cscore, sc);
+      const int rsplits = (int)std::max<int64_t>(1, ceil_div(kNumSMs * 12, L.n_tiles));
+      dim3 grid(L.n_tiles, rsplits);
+      k_rescore<<<grid, 256, rs_smem, st>>>(list, tile_off, L.list_cap, user0, (int)a->n_items, a->d, a->user_emb,
+                                            a->ld_user, a->user_ids, a->item_emb, a->ld_item, thr_exact,
+                                            a->seen_ptr, a->seen_items, flag, cnt, citem, cscore, sc);
       LGC_LAUNCH_CHECK();
+    }
+    {
+      ProfScope ps(PROF_SCORE_FINAL, st);
       k_select<<<(int)ceil_div((int64_t)nu * 32, 256), 256, 0, st>>>(nu, user0, (int)a->n_items, a->k, flag,
                                                                      cnt, citem, cscore, a->seen_ptr, a->seen_items,
                                                                      a->topk_items, a->topk_scores, fb, sc);
       LGC_LAUNCH_CHECK();
+    }
+    {
+      ProfScope ps(PROF_SCORE_EXHAUSTIVE, st);
       k_exhaustive<<<L.n_exh_ctas, 256, ex_smem, st>>>(fb, sc, user0, (int)a->n_items, a->d, a->k, a->user_emb,
                                                        a->ld_user, a->user_ids, a->item_emb, a->ld_item, a->seen_ptr,
                                                        a->seen_items, scratch, a->topk_items, a->topk_scores);

@@ -52,7 +52,8 @@ int lgc_ld_supported(int ld);
 /* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional
  * per-kernel-class timing with CUDA events recorded on the launching stream around each launch.
  * Tags: 0-3 light-row SpMM by epilogue {plain, fwd-init, fwd-rmw, adam}, 4-7 heavy-row SpMM,
- * 8-11 split-row finish, 12 BPR, 13 misc, 16-19 scoring {convert, gemm, select, rescore}.
+ * 8-11 split-row finish, 12 BPR, 13 misc, 16-22 scoring {convert, gemm, threshold, rescore,
+ * select, exhaustive, scan}.
  * lgc_profile_read synchronises the recorded events, sums milliseconds and launch counts per tag
  * into the HOST arrays and clears the record. */
 long long lgc_launch_count(void);
