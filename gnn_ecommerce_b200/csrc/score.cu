@@ -33,7 +33,7 @@ namespace {
 constexpr int kUserBlock = 256;   // users per CTA step (two M=128 halves)
 constexpr int kTileN = 128;       // items per MMA tile (N)
 constexpr int kGroup = 16;        // items per stored maximum
-constexpr int kCap = 64;          // exact candidates kept per user before falling back
+constexpr int kCap = 128;         // exact candidates kept per user before falling back
 constexpr int kGemmThreads = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr float kEpsRel = 0.0025f;  // > fp16 input rounding (2 * 2^-11) + fp16 output rounding (2^-11)
                                     //   + tensor-core fp32 accumulation slack, relative to |a||b|
@@ -239,7 +239,8 @@ __device__ __forceinline__ float group_max16(const uint32_t* v, int n_valid) {
 // Epilogue (8 warps, thread = user row): tcgen05.ld 16 columns at a time, maximum of each group of
 // 16 items; stored per group as an UPPER bound fp16((max + e) * out_scale) rounded up, and per tile
 // as a LOWER bound fp16((max - e) * out_scale) rounded down, e = eps_rel*|a_u|*max|b_tile| + eps_abs.
-//   gmax16 : [n_tiles*4][u_pad] uint32 = upper bounds of groups 2p (low half) and 2p+1 of a tile
+//   gmax16 : [n_tiles][u_pad][4] uint32 = upper bounds of groups 2p (low half) and 2p+1 of a tile;
+//            one 16-byte record per (tile, user): one STG.128 here, one LDG.128 in k_scan
 //   gtile  : [n_tiles][u_pad] uint32 = fp16 lower bound (low half) and upper bound (high half) of
 //            the tile maximum
 template <bool TS, int KATOMS>
@@ -414,13 +415,17 @@ k_score_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
         const float tm = fmaxf(max3(gm[0], gm[1], gm[2]), max3(max3(gm[3], gm[4], gm[5]), gm[6], gm[7]));
         if (dbg_mode == 2 && tm != 12345.678f) continue;   // timing experiment: no stores
-        uint32_t* g16 = gmax16 + (size_t)(t * 4) * u_pad + user;
+        uint4 rec;
+        {
+          uint32_t* rw = reinterpret_cast<uint32_t*>(&rec);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const __half2 hh = __halves2half2(__float2half_ru((gm[2 * p] + e) * out_scale),
-                                            __float2half_ru((gm[2 * p + 1] + e) * out_scale));
-          __stcs(g16 + (size_t)p * u_pad, *reinterpret_cast<const uint32_t*>(&hh));
+          for (int p = 0; p < 4; ++p) {
+            const __half2 hh = __halves2half2(__float2half_ru((gm[2 * p] + e) * out_scale),
+                                              __float2half_ru((gm[2 * p + 1] + e) * out_scale));
+            rw[p] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
         }
+        __stcs(reinterpret_cast<uint4*>(gmax16) + (size_t)t * u_pad + user, rec);
         {
           const __half2 hh = __halves2half2(__float2half_rd((tm - e) * out_scale),
                                             __float2half_ru((tm + e) * out_scale));
@@ -471,22 +476,35 @@ k_threshold(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gma
   extern __shared__ unsigned short s_keys[];   // [32][pitch]
   const int u0 = blockIdx.x * 32;
   const int n_sel = use_groups ? n_tiles * 8 : n_tiles;
-  for (int i = threadIdx.x; i < pitch * 32; i += 256) {
-    const int t = i >> 5, j = i & 31;
-    unsigned short key = 0;                    // padding: below every real key
-    if (t < n_sel) {
-      if (use_groups) {
-        const uint32_t w = gmax16[(size_t)(t >> 1) * u_pad + u0 + j];
-        const float up = __half2float(__ushort_as_half((unsigned short)((t & 1) ? (w >> 16) : (w & 0xFFFFu))));
-        const float e = fmaf(anorm[u0 + j] * kEpsRel, btile[t >> 3], eps_abs) * out_scale;
-        const float lo = up - 0.0009765625f * fabsf(up) - 2.f * e;
-        key = (unsigned short)key_of(__half_as_ushort(__float2half_rd(lo)));
-      } else {
-        key = (unsigned short)key_of((unsigned short)(gtile[(size_t)t * u_pad + u0 + j] & 0xFFFFu));
-      }
-      if (key == 0) key = 1;
+  for (int i0 = threadIdx.x; i0 < pitch * 32; i0 += 1024) {
+    uint32_t raw[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {                 // four loads in flight per thread
+      const int i = i0 + 256 * x, t = i >> 5, j = i & 31;
+      raw[x] = 0;
+      if (t < n_sel)
+        raw[x] = use_groups ? gmax16[((size_t)(t >> 3) * u_pad + u0 + j) * 4 + ((t >> 1) & 3)]
+                            : gtile[(size_t)t * u_pad + u0 + j];
     }
-    s_keys[j * pitch + t] = key;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int i = i0 + 256 * x, t = i >> 5, j = i & 31;
+      if (i >= pitch * 32) continue;
+      unsigned short key = 0;                    // padding: below every real key
+      if (t < n_sel) {
+        if (use_groups) {
+          const uint32_t w = raw[x];
+          const float up = __half2float(__ushort_as_half((unsigned short)((t & 1) ? (w >> 16) : (w & 0xFFFFu))));
+          const float e = fmaf(anorm[u0 + j] * kEpsRel, btile[t >> 3], eps_abs) * out_scale;
+          const float lo = up - 0.0009765625f * fabsf(up) - 2.f * e;
+          key = (unsigned short)key_of(__half_as_ushort(__float2half_rd(lo)));
+        } else {
+          key = (unsigned short)key_of((unsigned short)(raw[x] & 0xFFFFu));
+        }
+        if (key == 0) key = 1;
+      }
+      s_keys[j * pitch + t] = key;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -506,15 +524,35 @@ k_threshold(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gma
       }
       continue;
     }
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(s_keys + j * pitch);
+    const unsigned short* row = s_keys + j * pitch;
     unsigned prefix = 0;
-    for (int bit = 15; bit >= 0; --bit) {
-      const unsigned cand = prefix | (1u << bit);
-      const unsigned cand2 = cand | (cand << 16);
-      int cnt = 0;
-      for (int w = lane; w < n_words; w += 32) cnt += __popc(__vcmpgeu2(row[w], cand2));
-      cnt = __reduce_add_sync(0xffffffffu, cnt) >> 4;
-      if (cnt >= r) prefix = cand;
+    if (pitch <= 512) {                       // keys of this user in registers: 16 per lane
+      unsigned kreg[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int t = lane + 32 * i;
+        kreg[i] = t < pitch ? row[t] : 0u;
+      }
+      for (int bit = 15; bit >= 0; --bit) {
+        const unsigned cand = prefix | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cnt += kreg[i] >= cand ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= r) prefix = cand;
+      }
+    } else {
+      const uint32_t* row32 = reinterpret_cast<const uint32_t*>(row);
+      for (int bit = 15; bit >= 0; --bit) {
+        const unsigned cand = prefix | (1u << bit);
+        int cnt = 0;
+        for (int w = lane; w < n_words; w += 32) {
+          const uint32_t v = row32[w];
+          cnt += ((v & 0xFFFFu) >= cand ? 1 : 0) + ((v >> 16) >= cand ? 1 : 0);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= r) prefix = cand;
+      }
     }
     if (lane == 0) {
       const float T = __half2float(__ushort_as_half(bits_of(prefix)));      // stored units, lower bound
@@ -527,22 +565,8 @@ k_threshold(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gma
 }
 
 // ------------------------------------------------------------------------------------ exact re-scoring
-// Fixed summation order shared by the fast path and the exhaustive path (identical scores):
-// even float4 chunks into one accumulator, odd chunks into another, total = even + odd.
-__device__ __forceinline__ float dot_exact(const float4* __restrict__ a, const float4* __restrict__ b, int d4) {
-  float s0 = 0.f, s1 = 0.f;
-  int c = 0;
-  for (; c + 1 < d4; c += 2) {
-    const float4 x0 = a[c], y0 = b[c], x1 = a[c + 1], y1 = b[c + 1];
-    s0 = fmaf(x0.x, y0.x, s0); s0 = fmaf(x0.y, y0.y, s0); s0 = fmaf(x0.z, y0.z, s0); s0 = fmaf(x0.w, y0.w, s0);
-    s1 = fmaf(x1.x, y1.x, s1); s1 = fmaf(x1.y, y1.y, s1); s1 = fmaf(x1.z, y1.z, s1); s1 = fmaf(x1.w, y1.w, s1);
-  }
-  if (c < d4) {
-    const float4 x0 = a[c], y0 = b[c];
-    s0 = fmaf(x0.x, y0.x, s0); s0 = fmaf(x0.y, y0.y, s0); s0 = fmaf(x0.z, y0.z, s0); s0 = fmaf(x0.w, y0.w, s0);
-  }
-  return s0 + s1;
-}
+// Fixed summation order shared by k_rescore and k_exhaustive (identical scores): even float4
+// chunks into one accumulator, odd chunks into another, x/y/z/w in order, total = even + odd.
 __device__ __forceinline__ float4 load_row_f4(const float* __restrict__ row, int c, int d) {
   if (4 * c + 3 < d) return __ldg(reinterpret_cast<const float4*>(row + 4 * c));
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -552,103 +576,111 @@ __device__ __forceinline__ float4 load_row_f4(const float* __restrict__ row, int
   return v;
 }
 
-constexpr int kRowsPerWarp = 16;      // user rows a warp keeps in flight
 
-// Candidate (user, group) pairs bucketed by item tile, in two streaming passes over the stored
-// bounds: FILL == false counts the hits of every tile, FILL == true writes `(user << 3) | group`
-// into the tile's slice of `list` (slices from the prefix sum of the counts). A tile is looked at
+// Candidate (user, group) pairs bucketed by 16-item group, in two streaming passes over the
+// stored bounds: FILL == false counts the hits of every group, FILL == true writes the user index
+// into the group's slice of `list` (slices from the prefix sum of the counts). A tile is looked at
 // in detail (its four group words) only when its own upper bound reaches the user's threshold.
 // Entries that do not fit `list_cap` are dropped and their user is sent to the exhaustive path.
+// Four users per thread are in flight at once (the loop is latency-bound otherwise).
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, int u_pad, int n_users,
-       const float* __restrict__ thr_grp, int* __restrict__ tile_cnt, const int* __restrict__ tile_off,
-       int* __restrict__ tile_cur, int* __restrict__ list, int list_cap, uint8_t* __restrict__ flag) {
+       const float* __restrict__ thr_grp, int* __restrict__ grp_cnt, const int* __restrict__ grp_off,
+       int* __restrict__ grp_cur, int* __restrict__ list, int list_cap, uint8_t* __restrict__ flag) {
   const int tile = blockIdx.x;
-  const int per = (n_users + gridDim.y - 1) / gridDim.y;
+  const int per = round_up((n_users + gridDim.y - 1) / gridDim.y, 1024);
   const int u_beg = blockIdx.y * per, u_end = min(n_users, u_beg + per);
-  const int lane = threadIdx.x & 31;
-  int my = 0;
-  for (int u0 = u_beg; u0 < u_end; u0 += 256) {
-    const int u = u0 + threadIdx.x;
-    unsigned hits = 0;
-    if (u < u_end) {
-      const float thr = thr_grp[u];
-      const uint32_t tw = __ldcs(gtile + (size_t)tile * u_pad + u);
-      const float up = __half2float(__ushort_as_half((unsigned short)(tw >> 16)));
-      if (up >= thr) {
+  __shared__ int s_cnt[8];
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int my[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int u0 = u_beg; u0 < u_end; u0 += 1024) {
+    float thr[4]; uint32_t tw[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const uint32_t w = __ldcs(gmax16 + (size_t)(tile * 4 + p) * u_pad + u);
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
-          if (f.x >= thr) hits |= 1u << (2 * p);
-          if (f.y >= thr) hits |= 1u << (2 * p + 1);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int u = u0 + threadIdx.x + 256 * j;
+      thr[j] = INFINITY; tw[j] = 0xFC00FC00u;          // -inf bounds
+      if (u < u_end) { thr[j] = thr_grp[u]; tw[j] = __ldcs(gtile + (size_t)tile * u_pad + u); }
     }
-    const int c = __popc(hits);
-    if (!FILL) {
-      my += c;
-    } else {
-      int incl = c;                                   // warp-aggregated slot allocation
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+    for (int j = 0; j < 4; ++j) {
+      const int u = u0 + threadIdx.x + 256 * j;
+      const float up = __half2float(__ushort_as_half((unsigned short)(tw[j] >> 16)));
+      if (!(up >= thr[j])) continue;
+      unsigned hits = 0;
+      const uint4 rec = __ldcs(reinterpret_cast<const uint4*>(gmax16) + (size_t)tile * u_pad + u);
+      const uint32_t w[4] = {rec.x, rec.y, rec.z, rec.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[p]));
+        if (f.x >= thr[j]) hits |= 1u << (2 * p);
+        if (f.y >= thr[j]) hits |= 1u << (2 * p + 1);
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
-        int base = 0;
-        if (lane == 31) base = atomicAdd(&tile_cur[tile], total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = tile_off[tile] + base + incl - c;
+      if (!FILL) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) my[g] += (hits >> g) & 1;
+      } else {
         while (hits) {
           const int g = __ffs(hits) - 1;
           hits &= hits - 1;
-          if (pos < list_cap) list[pos] = (u << 3) | g;
+          const int pos = grp_off[tile * 8 + g] + atomicAdd(&grp_cur[tile * 8 + g], 1);
+          if (pos < list_cap) list[pos] = u;
           else flag[u] = 2;                            // picked up by k_select -> exhaustive path
-          ++pos;
         }
       }
     }
   }
   if (!FILL) {
-    my = __reduce_add_sync(0xffffffffu, my);
-    if (lane == 0 && my) atomicAdd(&tile_cnt[tile], my);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int v = __reduce_add_sync(0xffffffffu, my[g]);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[g], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&grp_cnt[tile * 8 + threadIdx.x], s_cnt[threadIdx.x]);
   }
 }
 
-// exclusive prefix sum of the per-tile counts (n_tiles is a few hundred to a few thousand)
-__global__ void k_tile_prefix(const int* __restrict__ tile_cnt, int n_tiles, int* __restrict__ tile_off,
-                              ScoreScalars* __restrict__ sc) {
+// exclusive prefix sum of the per-group counts (a few thousand values)
+__global__ void k_group_prefix(const int* __restrict__ grp_cnt, int n_groups, int* __restrict__ grp_off,
+                               ScoreScalars* __restrict__ sc) {
   __shared__ long long s_part[256];
-  const int per = (n_tiles + 255) / 256;
-  const int b = threadIdx.x * per, e = min(n_tiles, b + per);
+  const int per = (n_groups + 255) / 256;
+  const int b = min(n_groups, (int)threadIdx.x * per), e = min(n_groups, b + per);
   long long sum = 0;
-  for (int t = b; t < e; ++t) sum += tile_cnt[t];
+  for (int t = b; t < e; ++t) sum += grp_cnt[t];
   s_part[threadIdx.x] = sum;
   __syncthreads();
   if (threadIdx.x == 0) {
     long long run = 0;
     for (int i = 0; i < 256; ++i) { const long long v = s_part[i]; s_part[i] = run; run += v; }
     sc->n_groups += (unsigned long long)run;
+    grp_off[n_groups] = (int)min(run, (long long)0x7fffffff);
   }
   __syncthreads();
   long long run = s_part[threadIdx.x];
   for (int t = b; t < e; ++t) {
-    tile_off[t] = (int)min(run, (long long)0x7fffffff);
-    run += tile_cnt[t];
+    grp_off[t] = (int)min(run, (long long)0x7fffffff);
+    run += grp_cnt[t];
   }
-  if (threadIdx.x == 255) tile_off[n_tiles] = (int)min(run, (long long)0x7fffffff);
 }
 
-// grid (n_tiles, splits). The CTA keeps its 128 item rows (fp32) in shared memory and walks its
-// share of the tile's candidate list. Per step a warp takes 16 (user, group) pairs: their
-// metadata, then all 16 user rows, are requested before anything is used -- that is what hides
-// the HBM latency of these random 256-byte reads -- then every lane computes 8 exact fp32 dot
-// products (lane = item of the group, half-warp = 8 of the pairs).
-__global__ void __launch_bounds__(256, 3)
-k_rescore(const int* __restrict__ list, const int* __restrict__ tile_off, int list_cap, int64_t user0, int n_items,
+constexpr int kRowsPerWarp = 16;      // user rows a warp keeps in flight
+
+// grid (n_tiles, splits). The CTA keeps its 128 item rows (fp32) in shared memory and walks the
+// candidate lists of the tile's 8 groups. Per step a warp takes 16 users of ONE group: their
+// metadata, then all 16 user rows, are requested before anything is used (that hides the HBM
+// latency of these random 256-byte reads); lane = (item of the group, half-warp) then streams its
+// item row once and reuses every chunk for the 8 user rows of its half-warp -- shared-memory
+// traffic is what bounds this kernel, not the 64 FMAs per score.
+struct RescoreMeta {          // lanes 0..15 own one user of the step each
+  int u; int64_t uid, sb; float thr; int n_seen;
+};
+
+template <bool PIPE>
+__global__ void __launch_bounds__(256, 2)
+k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int list_cap, int64_t user0, int n_items,
           int d, const float* __restrict__ user_emb, int ld_user, const int64_t* __restrict__ user_ids,
           const float* __restrict__ item_emb, int ld_item, const float* __restrict__ thr_exact,
           const int64_t* __restrict__ seen_ptr, const int64_t* __restrict__ seen_items,
@@ -661,8 +693,7 @@ k_rescore(const int* __restrict__ list, const int* __restrict__ tile_off, int li
   float4* s_rows = s_items + 128 * row_f4;                              // [8 warps][16][d4]
 
   const int tile = blockIdx.x, item0 = tile * kTileN;
-  const int beg = min(tile_off[tile], list_cap), end = min(tile_off[tile + 1], list_cap);
-  if (beg >= end) return;
+  if (min(grp_off[tile * 8], list_cap) >= min(grp_off[tile * 8 + 8], list_cap)) return;
   for (int i = threadIdx.x; i < 128 * d4; i += 256) {
     const int r = i / d4, c = i % d4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -675,59 +706,115 @@ k_rescore(const int* __restrict__ list, const int* __restrict__ tile_off, int li
   float4* rows = s_rows + (size_t)warp * kRowsPerWarp * d4;
   unsigned long long my_emit = 0;
   const int step = gridDim.y * 8 * kRowsPerWarp;
-  for (int e0 = beg + (blockIdx.y * 8 + warp) * kRowsPerWarp; e0 < end; e0 += step) {
-    const int ne = min(kRowsPerWarp, end - e0);
-    // lanes 0..15 own one pair each: entry + per-user metadata
-    int ent = 0; int64_t uid = 0, sb = 0; float thr = INFINITY; int n_seen = 0;
-    if (lane < ne) {
-      ent = list[e0 + lane];
-      const int u = ent >> 3;
-      if (flag[u] == 0) {
-        uid = user_ids ? user_ids[user0 + u] : user0 + u;
-        thr = thr_exact[u];
-        if (seen_ptr) { sb = seen_ptr[user0 + u]; n_seen = (int)(seen_ptr[user0 + u + 1] - sb); }
+
+  auto load_meta = [&](int e0, int end) {
+    RescoreMeta m; m.u = 0; m.uid = 0; m.sb = 0; m.thr = INFINITY; m.n_seen = 0;
+    if (e0 < end && lane < min(kRowsPerWarp, end - e0)) {
+      m.u = list[e0 + lane];
+      if (flag[m.u] == 0) {
+        m.uid = user_ids ? user_ids[user0 + m.u] : user0 + m.u;
+        m.thr = thr_exact[m.u];
+        if (seen_ptr) { m.sb = seen_ptr[user0 + m.u]; m.n_seen = (int)(seen_ptr[user0 + m.u + 1] - m.sb); }
       }
     }
-    __syncwarp();
-    for (int c0 = 0; c0 < d4; c0 += 16) {             // half-warp hw stages rows hw, hw+2, ...
-      float4 v[kRowsPerWarp / 2];
-      const int c = c0 + it;
+    return m;
+  };
+  // half-warp hw requests float4 column c of rows hw, hw+2, ... (8 loads in flight per lane)
+  auto request_rows = [&](const RescoreMeta& m, int ne, int c, float4 (&v)[kRowsPerWarp / 2]) {
 #pragma unroll
-      for (int i = 0; i < kRowsPerWarp / 2; ++i) {
-        const int slot = 2 * i + hw;
-        const int64_t id = __shfl_sync(0xffffffffu, uid, slot);
-        if (slot < ne && c < d4) v[i] = load_row_f4(user_emb + (size_t)id * ld_user, c, d);
-      }
-#pragma unroll
-      for (int i = 0; i < kRowsPerWarp / 2; ++i) {
-        const int slot = 2 * i + hw;
-        if (slot < ne && c < d4) rows[slot * d4 + c] = v[i];
-      }
-    }
-    __syncwarp();
-#pragma unroll 1
     for (int i = 0; i < kRowsPerWarp / 2; ++i) {
       const int slot = 2 * i + hw;
-      const int e_ent = __shfl_sync(0xffffffffu, ent, slot);
-      const float e_thr = __shfl_sync(0xffffffffu, thr, slot);
-      const int64_t e_sb = __shfl_sync(0xffffffffu, sb, slot);
-      const int e_ns = __shfl_sync(0xffffffffu, n_seen, slot);
-      if (slot >= ne) continue;
-      const int u = e_ent >> 3, g = e_ent & 7;
-      const int local = g * kGroup + it, item = item0 + local;
-      const float sco = dot_exact(rows + slot * d4, s_items + local * row_f4, d4);
-      if (item < n_items && sco >= e_thr) {
-        bool seen = false;
-        for (int q = 0; q < e_ns; ++q) seen |= (seen_items[e_sb + q] == item);
-        if (!seen) {
-          const int pos = atomicAdd(&cand_cnt[u], 1);
-          if (pos < kCap) {
-            cand_item[(size_t)u * kCap + pos] = item;
-            cand_score[(size_t)u * kCap + pos] = sco + 0.f;      // -0.0 -> +0.0
-          }
+      const int64_t id = __shfl_sync(0xffffffffu, m.uid, slot);
+      if (slot < ne && c < d4) v[i] = load_row_f4(user_emb + (size_t)id * ld_user, c, d);
+    }
+  };
+  auto store_rows = [&](int ne, int c, const float4 (&v)[kRowsPerWarp / 2]) {
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+      const int slot = 2 * i + hw;
+      if (slot < ne && c < d4) rows[slot * d4 + c] = v[i];
+    }
+  };
+
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    const int beg = min(grp_off[tile * 8 + g], list_cap), end = min(grp_off[tile * 8 + g + 1], list_cap);
+    const int local = g * kGroup + it, item = item0 + local;
+    const float4* irow = s_items + local * row_f4;
+    int e0 = beg + (blockIdx.y * 8 + warp) * kRowsPerWarp;
+    if (e0 >= end) continue;
+    // software pipeline (PIPE: d <= 64, one float4 column per lane and row): metadata two steps
+    // ahead, user rows one step ahead, so neither latency is exposed behind the dot products
+    RescoreMeta m0 = load_meta(e0, end), m1 = load_meta(e0 + step, end);
+    float4 vreg[kRowsPerWarp / 2];
+    if (PIPE) request_rows(m0, min(kRowsPerWarp, end - e0), it, vreg);
+    for (; e0 < end; e0 += step) {
+      const int ne = min(kRowsPerWarp, end - e0);
+      __syncwarp();
+      if (PIPE) {
+        store_rows(ne, it, vreg);
+      } else {
+        for (int c0 = 0; c0 < d4; c0 += 16) {
+          request_rows(m0, ne, c0 + it, vreg);
+          store_rows(ne, c0 + it, vreg);
+        }
+      }
+      __syncwarp();
+      const int e1 = e0 + step;
+      if (PIPE && e1 < end) request_rows(m1, min(kRowsPerWarp, end - e1), it, vreg);
+      const RescoreMeta m2 = load_meta(e1 + step, end);
+      // 8 dot products per lane; even chunks -> s0, odd chunks -> s1 (the order of k_exhaustive)
+      float s0[kRowsPerWarp / 2], s1[kRowsPerWarp / 2];
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp / 2; ++i) s0[i] = s1[i] = 0.f;
+      int c = 0;
+      for (; c + 1 < d4; c += 2) {
+        const float4 y0 = irow[c], y1 = irow[c + 1];
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+          const float4 x0 = rows[(2 * i + hw) * d4 + c], x1 = rows[(2 * i + hw) * d4 + c + 1];
+          s0[i] = fmaf(x0.x, y0.x, s0[i]); s0[i] = fmaf(x0.y, y0.y, s0[i]);
+          s0[i] = fmaf(x0.z, y0.z, s0[i]); s0[i] = fmaf(x0.w, y0.w, s0[i]);
+          s1[i] = fmaf(x1.x, y1.x, s1[i]); s1[i] = fmaf(x1.y, y1.y, s1[i]);
+          s1[i] = fmaf(x1.z, y1.z, s1[i]); s1[i] = fmaf(x1.w, y1.w, s1[i]);
+        }
+      }
+      if (c < d4) {
+        const float4 y0 = irow[c];
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+          const float4 x0 = rows[(2 * i + hw) * d4 + c];
+          s0[i] = fmaf(x0.x, y0.x, s0[i]); s0[i] = fmaf(x0.y, y0.y, s0[i]);
+          s0[i] = fmaf(x0.z, y0.z, s0[i]); s0[i] = fmaf(x0.w, y0.w, s0[i]);
+        }
+      }
+      // emission in two phases so the 8 slot-allocating atomics of a lane overlap
+      int e_u[kRowsPerWarp / 2], pos[kRowsPerWarp / 2];
+      float sco[kRowsPerWarp / 2];
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+        const int slot = 2 * i + hw;
+        e_u[i] = __shfl_sync(0xffffffffu, m0.u, slot);
+        const float e_thr = __shfl_sync(0xffffffffu, m0.thr, slot);
+        const int e_ns = __shfl_sync(0xffffffffu, m0.n_seen, slot);
+        sco[i] = s0[i] + s1[i];
+        bool hit = slot < ne && item < n_items && sco[i] >= e_thr;
+        if (__any_sync(0xffffffffu, hit && e_ns > 0)) {          // seen lists are short and rare
+          const int64_t e_sb = __shfl_sync(0xffffffffu, m0.sb, slot);
+          if (hit)
+            for (int q = 0; q < e_ns; ++q) hit &= (seen_items[e_sb + q] != item);
+        }
+        pos[i] = hit ? atomicAdd(&cand_cnt[e_u[i]], 1) : kCap;
+      }
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp / 2; ++i) {
+        if (pos[i] < kCap) {
+          cand_item[(size_t)e_u[i] * kCap + pos[i]] = item;
+          cand_score[(size_t)e_u[i] * kCap + pos[i]] = sco[i] + 0.f;      // -0.0 -> +0.0
           ++my_emit;
         }
       }
+      m0 = m1; m1 = m2;
     }
   }
   if (my_emit) atomicAdd(&sc->n_emitted, my_emit);
@@ -989,9 +1076,9 @@ bool make_layout(int64_t n_users, int64_t n_items, int d, int k, Layout* L) {
   L->off_g16 = take((size_t)L->n_tiles * 4 * cp * 4);
   L->off_g128 = take((size_t)L->n_tiles * cp * 4);
   L->list_cap = (int)std::min<size_t>((size_t)0x7ffffff0, std::max<size_t>((size_t)1 << 16, cp * 40));
-  L->off_tcnt = take((size_t)(L->n_tiles + 1) * 4);
-  L->off_toff = take((size_t)(L->n_tiles + 1) * 4);
-  L->off_tcur = take((size_t)(L->n_tiles + 1) * 4);
+  L->off_tcnt = take((size_t)(L->n_tiles * 8 + 1) * 4);
+  L->off_toff = take((size_t)(L->n_tiles * 8 + 1) * 4);
+  L->off_tcur = take((size_t)(L->n_tiles * 8 + 1) * 4);
   L->off_list = take((size_t)L->list_cap * 4);
   L->off_thr_grp = take(cp * 4);
   L->off_thr_exact = take(cp * 4);
@@ -1082,7 +1169,8 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     LGC_CUDA(cudaFuncSetAttribute(k_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LGC_CUDA(cudaFuncSetAttribute(k_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LGC_CUDA(cudaFuncSetAttribute(k_rescore<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LGC_CUDA(cudaFuncSetAttribute(k_rescore<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
 
@@ -1163,15 +1251,15 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     }
     {
       ProfScope ps(PROF_SCORE_SCAN, st);
-      LGC_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(L.n_tiles + 1) * 4, st));
-      LGC_CUDA(cudaMemsetAsync(tile_cur, 0, (size_t)(L.n_tiles + 1) * 4, st));
+      LGC_CUDA(cudaMemsetAsync(tile_cnt, 0, (size_t)(L.n_tiles * 8 + 1) * 4, st));
+      LGC_CUDA(cudaMemsetAsync(tile_cur, 0, (size_t)(L.n_tiles * 8 + 1) * 4, st));
       const int ssplits = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(kNumSMs * 16, L.n_tiles),
-                                                                      ceil_div(nu, 256)));
+                                                                      ceil_div(nu, 1024)));
       dim3 sgrid(L.n_tiles, ssplits);
       k_scan<false><<<sgrid, 256, 0, st>>>(g128, g16, L.chunk_pad, nu, thr_grp, tile_cnt, tile_off, tile_cur, list,
                                           L.list_cap, flag);
       LGC_LAUNCH_CHECK();
-      k_tile_prefix<<<1, 256, 0, st>>>(tile_cnt, L.n_tiles, tile_off, sc);
+      k_group_prefix<<<1, 256, 0, st>>>(tile_cnt, L.n_tiles * 8, tile_off, sc);
       LGC_LAUNCH_CHECK();
       k_scan<true><<<sgrid, 256, 0, st>>>(g128, g16, L.chunk_pad, nu, thr_grp, tile_cnt, tile_off, tile_cur, list,
                                          L.list_cap, flag);
@@ -1181,9 +1269,16 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
       ProfScope ps(PROF_SCORE_RESCORE, st);
       const int rsplits = (int)std::max<int64_t>(1, ceil_div(kNumSMs * 12, L.n_tiles));
       dim3 grid(L.n_tiles, rsplits);
-      k_rescore<<<grid, 256, rs_smem, st>>>(list, tile_off, L.list_cap, user0, (int)a->n_items, a->d, a->user_emb,
-                                            a->ld_user, a->user_ids, a->item_emb, a->ld_item, thr_exact,
-                                            a->seen_ptr, a->seen_items, flag, cnt, citem, cscore, sc);
+      if (d4 <= 16)
+        k_rescore<true><<<grid, 256, rs_smem, st>>>(list, tile_off, L.list_cap, user0, (int)a->n_items, a->d,
+                                                    a->user_emb, a->ld_user, a->user_ids, a->item_emb, a->ld_item,
+                                                    thr_exact, a->seen_ptr, a->seen_items, flag, cnt, citem, cscore,
+                                                    sc);
+      else
+        k_rescore<false><<<grid, 256, rs_smem, st>>>(list, tile_off, L.list_cap, user0, (int)a->n_items, a->d,
+                                                     a->user_emb, a->ld_user, a->user_ids, a->item_emb, a->ld_item,
+                                                     thr_exact, a->seen_ptr, a->seen_items, flag, cnt, citem, cscore,
+                                                     sc);
       LGC_LAUNCH_CHECK();
     }
     {
