@@ -31,6 +31,13 @@ class TrainStepArgs(C.Structure):
                 ("workspace", c_vp), ("workspace_bytes", c_sz)]
 
 
+class SpmmEpilogue(C.Structure):
+    _fields_ = [("mode", c_i32), ("a0", c_f32), ("a1", c_f32), ("scale", c_f32), ("beta", c_f32),
+                ("y", c_vp), ("acc", c_vp), ("xrow", c_vp), ("addend", c_vp), ("p", c_vp), ("m", c_vp),
+                ("v", c_vp), ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("eps", c_f64),
+                ("step", c_i64)]
+
+
 class ScoreTopkArgs(C.Structure):
     _fields_ = [("d", c_i32), ("ld_user", c_i32), ("ld_item", c_i32), ("k", c_i32),
                 ("n_users", c_i64), ("n_items", c_i64), ("user_emb", c_vp), ("item_emb", c_vp),
@@ -48,10 +55,12 @@ _SIGNATURES = {
     "lgc_profile_enable": (C.c_int, [C.c_int]),
     "lgc_profile_read": (C.c_int, [C.POINTER(c_f64), C.POINTER(C.c_longlong), C.c_int]),
     "lgc_graph_build": (C.c_int, [c_i64, c_i64, c_vp, c_vp, C.c_int, c_vp, C.POINTER(c_vp)]),
+    "lgc_graph_build_rect": (C.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
     "lgc_graph_destroy": (C.c_int, [c_vp]),
     "lgc_graph_get_info": (C.c_int, [c_vp, C.POINTER(GraphInfo)]),
     "lgc_spmm_workspace_bytes": (c_sz, [c_vp, C.c_int]),
     "lgc_spmm": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lgc_spmm_ex": (C.c_int, [c_vp, C.c_int, c_vp, C.POINTER(SpmmEpilogue), c_vp, c_sz, c_vp]),
     "lgc_propagate_workspace_bytes": (c_sz, [c_vp, C.c_int, C.c_int]),
     "lgc_propagate": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_f32), c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgc_pair_scores": (C.c_int, [C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),

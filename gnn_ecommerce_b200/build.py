@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-lcuda", "-Xlinker", "--no-undefined"]
+            "-Xlinker", "--no-undefined"]      # no -lcuda: the .so must load without a driver
     subprocess.run(link, check=True)
     return LIB
 

@@ -44,14 +44,14 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 
 // keys = target id, vals = edge position; count in-degrees; range check; symmetry fingerprint
 __global__ void k_extract(const int64_t* __restrict__ ei, const float* __restrict__ ew, int64_t nnz,
-                          int64_t num_nodes, int32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                          int64_t num_nodes, int64_t num_cols, int32_t* __restrict__ keys, int32_t* __restrict__ vals,
                           int32_t* __restrict__ counts, int* __restrict__ bad,
                           unsigned long long* __restrict__ fp) {
   unsigned long long h_fwd = 0, h_rev = 0;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz;
        e += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = ei[e], c = ei[nnz + e];
-    if (r < 0 || r >= num_nodes || c < 0 || c >= num_nodes) {
+    if (r < 0 || r >= num_cols || c < 0 || c >= num_nodes) {
       atomicExch(bad, 1);
       keys[e] = 0; vals[e] = (int32_t)e;
       continue;
@@ -209,11 +209,27 @@ extern "C" int lgc_graph_get_info(const lgc_graph_t* g, lgc_graph_info* info) {
   return LGC_OK;
 }
 
+static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, const int64_t* ei, const float* ew,
+                            int normalize, void* stream_, lgc_graph_t** out);
+
 extern "C" int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* ei, const float* ew,
                                int normalize, void* stream_, lgc_graph_t** out) {
+  return graph_build_impl(num_nodes, num_nodes, nnz, ei, ew, normalize, stream_, out);
+}
+
+extern "C" int lgc_graph_build_rect(int64_t num_rows, int64_t num_cols, int64_t nnz, const int64_t* ei,
+                                    const float* ew, void* stream_, lgc_graph_t** out) {
+  return graph_build_impl(num_rows, num_cols, nnz, ei, ew, 0, stream_, out);
+}
+
+// rows = targets (row 1 of edge_index) in [0, num_nodes); sources (row 0) in [0, num_cols)
+static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, const int64_t* ei, const float* ew,
+                            int normalize, void* stream_, lgc_graph_t** out) {
   LGC_REQUIRE(out, "out_graph is null");
   *out = nullptr;
   LGC_REQUIRE(num_nodes > 0 && num_nodes < (1LL << 31) - 64, "num_nodes out of range");
+  LGC_REQUIRE(num_cols > 0 && num_cols < (1LL << 31) - 64, "num_cols out of range");
+  LGC_REQUIRE(!normalize || num_cols == num_nodes, "normalisation needs a square operator");
   LGC_REQUIRE(nnz >= 0 && nnz < (1LL << 31) - 64, "nnz out of range");
   LGC_REQUIRE(nnz == 0 || ei, "edge_index is null");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -227,8 +243,12 @@ extern "C" int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* ei
   DevBuf<int4> chunks, split_rows;
   const size_t n1 = (size_t)num_nodes + 1;
   LGC_CUDA(keys_in.alloc(nnz)); LGC_CUDA(keys_out.alloc(nnz)); LGC_CUDA(vals_in.alloc(nnz));
-  LGC_CUDA(eid.alloc(nnz)); LGC_CUDA(src.alloc(nnz)); LGC_CUDA(w.alloc(nnz));
-  LGC_CUDA(counts.alloc(n1)); LGC_CUDA(rowptr.alloc(n1));
+  // src / w_hat / rowptr are padded: the light-row SpMM bulk-copies 16-byte-granular supersets
+  LGC_CUDA(eid.alloc(nnz)); LGC_CUDA(src.alloc(nnz + 8)); LGC_CUDA(w.alloc(nnz + 8));
+  LGC_CUDA(cudaMemsetAsync(src.p + nnz, 0, 8 * sizeof(int32_t), stream));
+  LGC_CUDA(cudaMemsetAsync(w.p + nnz, 0, 8 * sizeof(float), stream));
+  LGC_CUDA(counts.alloc(n1)); LGC_CUDA(rowptr.alloc(n1 + 8));
+  LGC_CUDA(cudaMemsetAsync(rowptr.p + n1, 0, 8 * sizeof(int32_t), stream));
   LGC_CUDA(deg.alloc(num_nodes)); LGC_CUDA(dis.alloc(num_nodes));
   LGC_CUDA(bad.alloc(1)); LGC_CUDA(fp.alloc(2));
   LGC_CUDA(cudaMemsetAsync(counts.p, 0, n1 * sizeof(int32_t), stream));
@@ -237,7 +257,7 @@ extern "C" int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* ei
 
   const int threads = 256;
   const int grid_e = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(nnz, threads), 1), kNumSMs * 16);
-  k_extract<<<grid_e, threads, 0, stream>>>(ei, ew, nnz, num_nodes, keys_in.p, vals_in.p, counts.p,
+  k_extract<<<grid_e, threads, 0, stream>>>(ei, ew, nnz, num_nodes, num_cols, keys_in.p, vals_in.p, counts.p,
                                             bad.p, fp.p);
   LGC_LAUNCH_CHECK();
 
@@ -284,7 +304,7 @@ extern "C" int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* ei
   LGC_CUDA(cudaMemcpyAsync(h_fp, fp.p, 16, cudaMemcpyDeviceToHost, stream));
   LGC_CUDA(cudaStreamSynchronize(stream));
   if (h_bad) {
-    set_error("edge_index holds a node id outside [0, num_nodes)");
+    set_error("edge_index holds a node id outside [0, num_nodes)");   // (or a source outside [0, num_cols))
     return LGC_ERR_INDEX_RANGE;
   }
   LGC_CUDA(chunks.alloc(h_tot[0])); LGC_CUDA(split_rows.alloc(h_tot[2]));
@@ -297,7 +317,7 @@ extern "C" int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* ei
 
   lgc_graph* g = new lgc_graph();
   g->num_nodes = num_nodes; g->nnz = nnz;
-  g->is_symmetric = (h_fp[0] == h_fp[1]) ? 1 : 0;
+  g->is_symmetric = (num_cols == num_nodes && h_fp[0] == h_fp[1]) ? 1 : 0;
   g->light_max_degree = kLightMaxDegree;
   g->num_chunks = h_tot[0];
   g->num_partial_slots = h_tot[1];

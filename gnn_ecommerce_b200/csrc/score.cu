@@ -1097,14 +1097,27 @@ int encode_map(CUtensorMap* map, const void* base, int kp, int64_t rows) {
   cuuint64_t gstride[1] = {(cuuint64_t)kp * 2};
   cuuint32_t box[2] = {64, 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim,
-                                      gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // The driver entry point is resolved through the runtime, so the library has no link-time
+  // dependency on libcuda.so (it must load on a machine without a GPU driver).
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LGC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available in this driver");
+      return LGC_ERR_CUDA;
+    }
+    encode = (EncodeFn)fn;
+  }
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    const char* s = nullptr;
-    cuGetErrorString(r, &s);
-    set_error(std::string("cuTensorMapEncodeTiled: ") + (s ? s : "?"));
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return LGC_ERR_CUDA;
   }
   return LGC_OK;

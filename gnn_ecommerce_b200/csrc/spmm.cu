@@ -12,6 +12,8 @@
 //   finish: split rows add their partials in order and apply the epilogue.
 // The epilogue fuses what the reference runs as separate ATen passes: the running layer mean
 // `out = out + x * alpha` (src/lightgcn.py:93,97), the backward Horner add, and dense Adam.
+#include <algorithm>
+
 #include "spmm.cuh"
 
 namespace lgc {
@@ -82,105 +84,287 @@ __device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s)
 }
 
 // ---------------------------------------------------------------------------------- light rows
-// One CTA = a tile of consecutive rows. The tile's rowptr slice and (when it fits) its contiguous
-// CSR slice of (source, weight) pairs are staged in shared memory with two coalesced rounds, so a
-// row costs ONE exposed memory latency (its gathers, issued together with its epilogue operands)
-// instead of four dependent ones (rowptr -> indices -> gathers -> epilogue operands). Each L-lane
-// sub-warp walks its rows two at a time to double the loads in flight.
-constexpr int kLightRowsPerSub = 8;
-constexpr int kLightStageCap = 2048;   // staged CSR entries per tile (16 KB)
+// Persistent, warp-autonomous: no CTA barrier anywhere. Every warp walks its own sequence of row
+// tiles (TR consecutive rows, ~4 KB per operand). The epilogue operands of a tile (x / acc /
+// addend / p, m, v rows) are CONTIGUOUS in HBM, so threads never load them: lane 0 issues
+// bulk-async copies (cp.async.bulk, the TMA engine) of whole tiles into the warp's two-stage
+// shared-memory ring, two tiles ahead; the warp meanwhile reads the tile's CSR slice and runs the
+// gathers (neighbour rows; for user rows these are item rows that live in L2) into registers, then
+// applies the epilogue in shared memory in place, and lane 0 sends the result tiles back with
+// bulk-async stores. Dozens of KB per SM are in flight without holding a register, and writes
+// leave as whole lines. Rows above `light_max` keep their shared-memory slots untouched
+// (read-modify-write operands are stored back unchanged, plain outputs are overwritten by the
+// heavy-row kernels that run after this one on the same stream).
+constexpr int kLightWarps = 4;         // warps per CTA (each fully independent)
+constexpr int kLightStageCap = 128;    // CSR entries of a tile staged per warp and stage
 
 template <int L, int V, int MODE>
-__global__ void __launch_bounds__(256) k_spmm_light(const int32_t* __restrict__ rowptr,
-                                                    const int32_t* __restrict__ src,
-                                                    const float* __restrict__ w,
-                                                    const float* __restrict__ x, int num_rows,
-                                                    int light_max, EpiArgs args) {
-  constexpr int LD = 4 * L * V;
-  constexpr int NSUB = 256 / L;                       // sub-warps per CTA
-  constexpr int TILE = NSUB * kLightRowsPerSub;       // rows per CTA
-  __shared__ int s_rp[TILE + 1];
-  __shared__ int s_src[kLightStageCap];
-  __shared__ float s_w[kLightStageCap];
+struct LightCfg {
+  static constexpr int LD = 4 * L * V;
+  static constexpr int NSUBW = 32 / L;                                  // sub-warps per warp
+  static constexpr int RPS0 = (MODE == EPI_ADAM ? 256 : 512) / LD / NSUBW;
+  static constexpr int RPS = RPS0 >= 8 ? 8 : (RPS0 >= 4 ? 4 : 2);      // rows per sub-warp and tile
+  static constexpr int TR = RPS * NSUBW;                                // rows per tile (multiple of 4)
+  static constexpr int NBUF = MODE == EPI_ADAM ? 4 : (MODE == EPI_PLAIN ? 1 : 2);
+  static constexpr int TILE_FLOATS = TR * LD;
+  static constexpr int RP_INTS = TR + 4;                                // rowptr slice, 16-byte granular
+  static constexpr int CSR_INTS = kLightStageCap + 4;                   // aligned superset of the slice
+  // per stage: operand tiles | rowptr slice | src slice | w slice
+  static constexpr size_t STAGE_BYTES = (size_t)NBUF * TILE_FLOATS * 4 + RP_INTS * 4 + 2 * CSR_INTS * 4;
+  static constexpr size_t WARP_BYTES = 2 * STAGE_BYTES + 64;            // + 6 mbarriers
+  static constexpr size_t SMEM = kLightWarps * WARP_BYTES + 128;
+};
 
-  const int row0 = blockIdx.x * TILE;
-  for (int t = threadIdx.x; t <= TILE; t += 256) s_rp[t] = rowptr[min(row0 + t, num_rows)];
-  __syncthreads();
-  const int e0 = s_rp[0], n_e = s_rp[TILE] - e0;
-  const bool staged = n_e <= kLightStageCap;
-  if (staged) {
-    for (int i = threadIdx.x; i < n_e; i += 256) { s_src[i] = src[e0 + i]; s_w[i] = w[e0 + i]; }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Tile streams are touched once per launch: evict-first in L2, so they do not push the gather
+// sources (the item table, L2-resident) out.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar,
+                                          uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(gdst), "r"(smem_addr(smem_src)), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// Requires rowptr / src / w allocations padded by >= 8 elements (graph build does that): the
+// bulk copies move 16-byte-granular supersets of the slices they need.
+template <int L, int V, int MODE>
+__global__ void __launch_bounds__(32 * kLightWarps)
+k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ w,
+             const float* __restrict__ x, int num_rows, int light_max, EpiArgs args) {
+  using C = LightCfg<L, V, MODE>;
+  constexpr int LD = C::LD, NSUBW = C::NSUBW, RPS = C::RPS, TR = C::TR, NBUF = C::NBUF, TF = C::TILE_FLOATS;
+  extern __shared__ __align__(128) uint8_t smem_light[];
+  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_light) + 127) & ~(uintptr_t)127) +
+                   (size_t)wic * C::WARP_BYTES;
+  auto stage_tiles = [&](int st) { return reinterpret_cast<float*>(wbase + (size_t)st * C::STAGE_BYTES); };
+  auto stage_rp = [&](int st) { return reinterpret_cast<int*>(stage_tiles(st) + NBUF * TF); };
+  auto stage_src = [&](int st) { return stage_rp(st) + C::RP_INTS; };
+  auto stage_w = [&](int st) { return reinterpret_cast<float*>(stage_src(st) + C::CSR_INTS); };
+  // barriers: [0..1] operand tiles, [2..3] rowptr slice, [4..5] CSR slice (index + stage)
+  const uint32_t bar0 = smem_addr(wbase + 2 * C::STAGE_BYTES);
+  const uint64_t pol = policy_evict_first();
+
+  const int n_tiles = (num_rows + TR - 1) / TR;
+  const int gw = blockIdx.x * kLightWarps + wic, nw = gridDim.x * kLightWarps;
+  const float* in0 = MODE == EPI_PLAIN ? args.addend : (MODE == EPI_FWD_INIT ? args.xrow
+                    : (MODE == EPI_FWD_RMW ? args.acc : args.addend));
+  const uint32_t n_in = (in0 ? 1u : 0u) + (MODE == EPI_ADAM ? 3u : 0u);
+
+  // lane 0: operand tiles + rowptr slice of `tile` -> ring stage `st` (two tiles ahead)
+  auto request_tile = [&](int tile, int st) {
+    if (tile >= n_tiles) return;
+    const int row0 = tile * TR;
+    const int rows = min(TR, num_rows - row0);
+    const uint32_t rp_bytes = (uint32_t)((rows + 1 + 3) & ~3) * 4;
+    mbar_expect(bar0 + 8u * (2 + st), rp_bytes);
+    bulk_load(stage_rp(st), rowptr + row0, rp_bytes, bar0 + 8u * (2 + st), pol);
+    if (n_in == 0) return;
+    const uint32_t bytes = (uint32_t)rows * LD * 4;
+    const size_t goff = (size_t)row0 * LD;
+    float* b = stage_tiles(st);
+    const uint32_t bar = bar0 + 8u * st;
+    mbar_expect(bar, n_in * bytes);
+    if (in0) bulk_load(b, in0 + goff, bytes, bar, pol);
+    if (MODE == EPI_ADAM) {
+      bulk_load(b + TF, args.p + goff, bytes, bar, pol);
+      bulk_load(b + 2 * TF, args.m + goff, bytes, bar, pol);
+      bulk_load(b + 3 * TF, args.v + goff, bytes, bar, pol);
+    }
+  };
+  // lane 0: once the rowptr slice of `tile` (use count `k` of stage `st`) has landed, request the
+  // 16-byte-aligned superset of its (src, w) slice (one tile ahead)
+  auto request_csr = [&](int tile, int st, int k) {
+    if (tile >= n_tiles) return;
+    mbar_wait_parity(bar0 + 8u * (2 + st), (uint32_t)(k >> 1) & 1u);
+    const int rows = min(TR, num_rows - tile * TR);
+    const int* rp = stage_rp(st);
+    const int e0 = rp[0], e1 = rp[rows];
+    const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
+    if (a1 - a0 > C::CSR_INTS || a1 == a0) return;          // too long (read from global) or empty
+    const uint32_t bytes = (uint32_t)(a1 - a0) * 4;
+    mbar_expect(bar0 + 8u * (4 + st), 2 * bytes);
+    bulk_load(stage_src(st), src + a0, bytes, bar0 + 8u * (4 + st), pol);
+    bulk_load(stage_w(st), w + a0, bytes, bar0 + 8u * (4 + st), pol);
+  };
+  if (lane == 0) {
+    for (int b = 0; b < 6; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    request_tile(gw, 0);
+    request_tile(gw + nw, 1);
+    request_csr(gw, 0, 0);
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int sw = threadIdx.x / L, sl = threadIdx.x % L;
-#pragma unroll 1
-  for (int j = 0; j < kLightRowsPerSub; j += 2) {
-    // consecutive sub-warps take consecutive rows: a warp's stores are contiguous
-    const int ta = j * NSUB + sw, tb = ta + NSUB;
-    const int rowa = row0 + ta, rowb = row0 + tb;
-    int bega = s_rp[ta], dega = s_rp[ta + 1] - bega;
-    int begb = s_rp[tb], degb = s_rp[tb + 1] - begb;
-    const bool oka = rowa < num_rows && dega <= light_max;
-    const bool okb = rowb < num_rows && degb <= light_max;
-    if (!oka) dega = 0;
-    if (!okb) degb = 0;
-    const size_t offa = (size_t)rowa * LD + 4 * sl, offb = (size_t)rowb * LD + 4 * sl;
-    Pre qa[V], qb[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (oka) epi_preload<MODE>(args, offa + 4 * L * v, qa[v]);
-      if (okb) epi_preload<MODE>(args, offb + 4 * L * v, qb[v]);
+  const int sw = lane / L, sl = lane % L;
+  int k = 0;
+  uint32_t csr_par = 0;                                  // phase parity of the two CSR barriers
+  for (int tile = gw; tile < n_tiles; tile += nw, ++k) {
+    const int st = k & 1;
+    const uint32_t par = (uint32_t)(k >> 1) & 1u;
+    const int row0 = tile * TR;
+    const int rows_here = min(TR, num_rows - row0);
+    float* buf0 = stage_tiles(st);
+    float* buf1 = buf0 + (NBUF > 1 ? TF : 0);
+    float* buf2 = buf0 + (NBUF > 2 ? 2 * TF : 0);
+    float* buf3 = buf0 + (NBUF > 3 ? 3 * TF : 0);
+    const int* s_rp = stage_rp(st);
+    const int* s_src = stage_src(st);
+    const float* s_w = stage_w(st);
+
+    // ---- the tile's rowptr slice and (when it fits) its CSR slice: already in shared memory
+    mbar_wait_parity(bar0 + 8u * (2 + st), par);
+    const int e0 = s_rp[0], n_e = s_rp[rows_here] - e0;
+    const int a0 = e0 & ~3, a1 = (e0 + n_e + 3) & ~3;   // staged entries start at the aligned edge
+    const bool staged = (a1 - a0 <= C::CSR_INTS) && (a1 != a0);   // == "request_csr issued a copy"
+    if (staged) {                                        // this barrier only advances when used
+      mbar_wait_parity(bar0 + 8u * (4 + st), (csr_par >> st) & 1u);
+      csr_par ^= 1u << st;
     }
-    float4 acca[V], accb[V];
+
+    // ---- gathers: sub-warp `sw` owns tile rows sw, sw+NSUBW, ..., two rows at a time, EU edges
+    // per row and step: 2*EU*V 128-bit loads in flight per lane
+    constexpr int EU = V >= 3 ? 1 : 2;
+    float4 acc[RPS][V];
+    bool ok[RPS];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acca[v] = accb[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int dmax = max(dega, degb);
-    for (int t = 0; t < dmax; t += 2) {
-      int sa[2], sb[2]; float wa[2], wb[2]; float4 xa[2][V], xb[2][V];
+    for (int j0 = 0; j0 < RPS; j0 += 2) {
+      int beg[2], deg[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (t + u < dega) {
-          const int e = bega + t + u;
-          sa[u] = staged ? s_src[e - e0] : src[e];
-          wa[u] = staged ? s_w[e - e0] : w[e];
-        }
-        if (t + u < degb) {
-          const int e = begb + t + u;
-          sb[u] = staged ? s_src[e - e0] : src[e];
-          wb[u] = staged ? s_w[e - e0] : w[e];
+      for (int q = 0; q < 2; ++q) {
+        const int t = (j0 + q) * NSUBW + sw;
+        ok[j0 + q] = t < rows_here;
+        beg[q] = ok[j0 + q] ? s_rp[t] : 0;
+        deg[q] = ok[j0 + q] ? s_rp[t + 1] - beg[q] : 0;
+        ok[j0 + q] = ok[j0 + q] && deg[q] <= light_max;
+        if (!ok[j0 + q]) deg[q] = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[j0 + q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const int dmax = max(deg[0], deg[1]);
+      for (int t = 0; t < dmax; t += EU) {
+        int sidx[2][EU]; float wv[2][EU]; float4 xv[2][EU][V];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int u = 0; u < EU; ++u)
+            if (t + u < deg[q]) {
+              const int e = beg[q] + t + u;
+              sidx[q][u] = staged ? s_src[e - a0] : src[e];
+              wv[q][u] = staged ? s_w[e - a0] : w[e];
+            }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int u = 0; u < EU; ++u)
+            if (t + u < deg[q]) {
+              const float* xr = x + (size_t)sidx[q][u] * LD + 4 * sl;
+#pragma unroll
+              for (int v = 0; v < V; ++v) xv[q][u][v] = ldg_f4(xr + 4 * L * v);
+            }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int u = 0; u < EU; ++u)         // edge order kept per row
+            if (t + u < deg[q]) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc[j0 + q][v] = fma4(wv[q][u], xv[q][u][v], acc[j0 + q][v]);
+            }
+      }
+    }
+
+    // ---- epilogue in shared memory (same arithmetic as epi_finish), in place
+    if (n_in) mbar_wait_parity(bar0 + 8u * st, par);
+#pragma unroll
+    for (int j = 0; j < RPS; ++j) {
+      if (!ok[j]) continue;
+      const int t = j * NSUBW + sw;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int off = t * LD + 4 * (sl + L * v);
+        const float4 s = acc[j][v];
+        if (MODE == EPI_PLAIN) {
+          float4 r = make_float4(args.scale * s.x, args.scale * s.y, args.scale * s.z, args.scale * s.w);
+          if (args.addend) {
+            const float4 q = ld_f4(buf0 + off);
+            r.x = fmaf(args.beta, q.x, r.x); r.y = fmaf(args.beta, q.y, r.y);
+            r.z = fmaf(args.beta, q.z, r.z); r.w = fmaf(args.beta, q.w, r.w);
+          }
+          st_f4(buf0 + off, r);
+        } else if (MODE == EPI_FWD_INIT) {
+          const float4 q = ld_f4(buf0 + off);
+          if (args.y) st_f4(buf1 + off, s);
+          float4 r;                              // out = x * alpha0; out = out + x1 * alpha1
+          r.x = __fadd_rn(__fmul_rn(q.x, args.a0), __fmul_rn(s.x, args.a1));
+          r.y = __fadd_rn(__fmul_rn(q.y, args.a0), __fmul_rn(s.y, args.a1));
+          r.z = __fadd_rn(__fmul_rn(q.z, args.a0), __fmul_rn(s.z, args.a1));
+          r.w = __fadd_rn(__fmul_rn(q.w, args.a0), __fmul_rn(s.w, args.a1));
+          st_f4(buf0 + off, r);
+        } else if (MODE == EPI_FWD_RMW) {
+          float4 o = ld_f4(buf0 + off);
+          if (args.y) st_f4(buf1 + off, s);
+          o.x = __fadd_rn(o.x, __fmul_rn(s.x, args.a1)); o.y = __fadd_rn(o.y, __fmul_rn(s.y, args.a1));
+          o.z = __fadd_rn(o.z, __fmul_rn(s.z, args.a1)); o.w = __fadd_rn(o.w, __fmul_rn(s.w, args.a1));
+          st_f4(buf0 + off, o);
+        } else {  // EPI_ADAM
+          const float4 z = ld_f4(buf0 + off);
+          float4 p = ld_f4(buf1 + off), m = ld_f4(buf2 + off), vv = ld_f4(buf3 + off);
+          adam_update(p.x, m.x, vv.x, fmaf(args.scale, s.x, z.x), args.adam);
+          adam_update(p.y, m.y, vv.y, fmaf(args.scale, s.y, z.y), args.adam);
+          adam_update(p.z, m.z, vv.z, fmaf(args.scale, s.z, z.z), args.adam);
+          adam_update(p.w, m.w, vv.w, fmaf(args.scale, s.w, z.w), args.adam);
+          st_f4(buf1 + off, p);
+          st_f4(buf2 + off, m);
+          st_f4(buf3 + off, vv);
         }
       }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (t + u < dega) {
-          const float* xr = x + (size_t)sa[u] * LD + 4 * sl;
-#pragma unroll
-          for (int v = 0; v < V; ++v) xa[u][v] = ldg_f4(xr + 4 * L * v);
-        }
-        if (t + u < degb) {
-          const float* xr = x + (size_t)sb[u] * LD + 4 * sl;
-#pragma unroll
-          for (int v = 0; v < V; ++v) xb[u][v] = ldg_f4(xr + 4 * L * v);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (t + u < dega) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) acca[v] = fma4(wa[u], xa[u][v], acca[v]);
-        }
-        if (t + u < degb) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) accb[v] = fma4(wb[u], xb[u][v], accb[v]);
-        }
-      }
     }
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (oka) epi_finish<MODE>(args, offa + 4 * L * v, acca[v], qa[v]);
-      if (okb) epi_finish<MODE>(args, offb + 4 * L * v, accb[v], qb[v]);
+
+    // ---- result tiles: shared memory -> HBM, asynchronously; then refill this ring stage
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)rows_here * LD * 4;
+      const size_t goff = (size_t)row0 * LD;
+      if (MODE == EPI_PLAIN) {
+        bulk_store(args.y + goff, buf0, bytes, pol);
+      } else if (MODE == EPI_ADAM) {
+        bulk_store(args.p + goff, buf1, bytes, pol);
+        bulk_store(args.m + goff, buf2, bytes, pol);
+        bulk_store(args.v + goff, buf3, bytes, pol);
+      } else {
+        bulk_store(args.acc + goff, buf0, bytes, pol);
+        if (args.y) bulk_store(args.y + goff, buf1, bytes, pol);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      request_csr(tile + nw, st ^ 1, k + 1);                              // next tile's CSR slice
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // stage readable again
+      request_tile(tile + 2 * nw, st);
     }
+    __syncwarp();
   }
 }
 
@@ -287,15 +471,28 @@ __global__ void __launch_bounds__(256) k_spmm_finish(const int4* __restrict__ sp
   for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
 }
 
-template <int L, int V, int MODE>
+// L, V: row geometry of the heavy-row kernels (widest sub-warp); LL, LV: of the light-row kernel
+// (few lanes per row: more rows per warp instruction, more gathers in flight per lane)
+template <int L, int V, int LL, int LV, int MODE>
 int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
   const int threads = 256, wpb = threads / 32;
   const int64_t n = g->num_nodes;
-  const int grid_light = (int)ceil_div(n, (256 / L) * kLightRowsPerSub);
+  using LC = LightCfg<LL, LV, MODE>;
   {
+    static int grid_light = 0;           // per instantiation: persistent grid = SMs x resident CTAs
+    if (!grid_light) {
+      LGC_CUDA(cudaFuncSetAttribute(k_spmm_light<LL, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)LC::SMEM));
+      int occ = 0;
+      LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_light<LL, LV, MODE>, 32 * kLightWarps,
+                                                             LC::SMEM));
+      grid_light = kNumSMs * (occ > 0 ? occ : 1);
+    }
+    const int n_tiles = (int)ceil_div(n, LC::TR);
+    const int grid = (int)std::min<int64_t>(grid_light, ceil_div(n_tiles, kLightWarps));
     ProfScope ps(PROF_LIGHT + MODE, st);
-    k_spmm_light<L, V, MODE><<<grid_light, threads, 0, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
-                                                              g->light_max_degree, a);
+    k_spmm_light<LL, LV, MODE><<<grid, 32 * kLightWarps, LC::SMEM, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
+                                                                        g->light_max_degree, a);
   }
   LGC_LAUNCH_CHECK();
   if (g->num_chunks > 0) {
@@ -319,14 +516,14 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   return LGC_OK;
 }
 
-template <int L, int V>
+template <int L, int V, int LL, int LV>
 int launch_mode(const lgc_graph* g, const float* x, EpiMode mode, const EpiArgs& a, float* partials,
                 cudaStream_t st) {
   switch (mode) {
-    case EPI_PLAIN: return launch_lv<L, V, EPI_PLAIN>(g, x, a, partials, st);
-    case EPI_FWD_INIT: return launch_lv<L, V, EPI_FWD_INIT>(g, x, a, partials, st);
-    case EPI_FWD_RMW: return launch_lv<L, V, EPI_FWD_RMW>(g, x, a, partials, st);
-    case EPI_ADAM: return launch_lv<L, V, EPI_ADAM>(g, x, a, partials, st);
+    case EPI_PLAIN: return launch_lv<L, V, LL, LV, EPI_PLAIN>(g, x, a, partials, st);
+    case EPI_FWD_INIT: return launch_lv<L, V, LL, LV, EPI_FWD_INIT>(g, x, a, partials, st);
+    case EPI_FWD_RMW: return launch_lv<L, V, LL, LV, EPI_FWD_RMW>(g, x, a, partials, st);
+    case EPI_ADAM: return launch_lv<L, V, LL, LV, EPI_ADAM>(g, x, a, partials, st);
   }
   return LGC_ERR_INVALID;
 }
@@ -352,12 +549,14 @@ int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const 
     set_error("unsupported row width ld=" + std::to_string(ld));
     return LGC_ERR_UNSUPPORTED;
   }
-#define LGC_CASE(LL, VV) \
-  if (rs.L == LL && rs.V == VV) return launch_mode<LL, VV>(g, x, mode, a, partials, st);
-  LGC_CASE(16, 1) LGC_CASE(16, 2) LGC_CASE(16, 3) LGC_CASE(16, 4)
-  LGC_CASE(8, 1) LGC_CASE(8, 3) LGC_CASE(8, 5)
-  LGC_CASE(4, 1) LGC_CASE(4, 3) LGC_CASE(4, 5)
-  LGC_CASE(2, 1) LGC_CASE(1, 1)
+#define LGC_CASE(HL, HV, LL, LV) \
+  if (rs.L == HL && rs.V == HV) return launch_mode<HL, HV, LL, LV>(g, x, mode, a, partials, st);
+  // light-row geometry == heavy-row geometry: narrower sub-warps (4 lanes x 4 float4) measured
+  // 1.5x slower -- 8 rows per warp instruction hit the same shared-memory banks in the epilogue
+  LGC_CASE(16, 1, 16, 1) LGC_CASE(16, 2, 16, 2) LGC_CASE(16, 3, 16, 3) LGC_CASE(16, 4, 16, 4)
+  LGC_CASE(8, 1, 8, 1) LGC_CASE(8, 3, 8, 3) LGC_CASE(8, 5, 8, 5)
+  LGC_CASE(4, 1, 4, 1) LGC_CASE(4, 3, 4, 3) LGC_CASE(4, 5, 4, 5)
+  LGC_CASE(2, 1, 2, 1) LGC_CASE(1, 1, 1, 1)
 #undef LGC_CASE
   set_error("no kernel instantiation for ld=" + std::to_string(ld));
   return LGC_ERR_UNSUPPORTED;
@@ -392,6 +591,30 @@ extern "C" int lgc_spmm(const lgc_graph_t* g, int ld, const float* x, float* y, 
   EpiArgs a;
   a.y = y;
   return launch_spmm(g, ld, x, EPI_PLAIN, a, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int lgc_spmm_ex(const lgc_graph_t* g, int ld, const float* x, const lgc_spmm_epilogue* e,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  LGC_REQUIRE(g && x && e, "null argument");
+  if (workspace_bytes < lgc_spmm_workspace_bytes(g, ld)) {
+    set_error("lgc_spmm_ex: workspace too small");
+    return LGC_ERR_WORKSPACE;
+  }
+  EpiArgs a;
+  a.y = e->y; a.acc = e->acc; a.xrow = e->xrow; a.addend = e->addend;
+  a.a0 = e->a0; a.a1 = e->a1; a.scale = e->scale; a.beta = e->beta;
+  a.p = e->p; a.m = e->m; a.v = e->v;
+  switch (e->mode) {
+    case LGC_EPI_PLAIN: LGC_REQUIRE(e->y && e->y != x, "PLAIN needs y (not aliasing x)"); break;
+    case LGC_EPI_FWD_INIT: LGC_REQUIRE(e->acc && e->xrow, "FWD_INIT needs acc and xrow"); break;
+    case LGC_EPI_FWD_RMW: LGC_REQUIRE(e->acc, "FWD_RMW needs acc"); break;
+    case LGC_EPI_ADAM:
+      LGC_REQUIRE(e->addend && e->p && e->m && e->v && e->step >= 1, "ADAM needs addend, p, m, v, step >= 1");
+      a.adam = make_adam_scalars(e->lr, e->beta1, e->beta2, e->eps, e->step);
+      break;
+    default: LGC_REQUIRE(false, "unknown epilogue mode");
+  }
+  return launch_spmm(g, ld, x, (EpiMode)e->mode, a, (float*)workspace, (cudaStream_t)stream);
 }
 
 extern "C" size_t lgc_propagate_workspace_bytes(const lgc_graph_t* g, int ld, int num_layers) {

@@ -77,6 +77,13 @@ int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* d_edge_index,
                     lgc_graph_t** out_graph);
 int lgc_graph_destroy(lgc_graph_t* graph);
 
+/* Rectangular operator for the row-partitioned multi-GPU path: rows = targets in [0, num_rows)
+ * (a GPU's shard of destination nodes, ids shifted to the shard), sources in [0, num_cols) (ids
+ * into the all-gathered table). Weights are used as given -- pass the w_hat of the global graph
+ * (lgc_graph_get_info().w_hat / eid) so every shard carries the global normalisation. */
+int lgc_graph_build_rect(int64_t num_rows, int64_t num_cols, int64_t nnz, const int64_t* d_edge_index,
+                         const float* d_edge_weight, void* stream, lgc_graph_t** out_graph);
+
 typedef struct {
   int64_t num_nodes;
   int64_t nnz;
@@ -102,6 +109,30 @@ int lgc_graph_get_info(const lgc_graph_t* graph, lgc_graph_info* info);
 size_t lgc_spmm_workspace_bytes(const lgc_graph_t* graph, int ld);
 int lgc_spmm(const lgc_graph_t* graph, int ld, const float* x, float* y, void* workspace,
              size_t workspace_bytes, void* stream);
+
+/* One LGConv layer with a fused epilogue (the building block of lgc_propagate / lgc_train_step,
+ * exported for the sharded multi-GPU driver, which interleaves layers with NCCL all-gathers):
+ *   s = (A_hat x)[r] for every row r of the graph (x: [num_cols, ld]; all other tables: [rows, ld])
+ *   LGC_EPI_PLAIN    y = scale * s + beta * addend            (addend may be NULL)
+ *   LGC_EPI_FWD_INIT acc = a0 * xrow + a1 * s;  y = s if y != NULL
+ *   LGC_EPI_FWD_RMW  acc = acc + a1 * s;        y = s if y != NULL
+ *   LGC_EPI_ADAM     g = scale * s + addend; torch.optim.Adam update of p, m, v with g */
+typedef enum { LGC_EPI_PLAIN = 0, LGC_EPI_FWD_INIT = 1, LGC_EPI_FWD_RMW = 2, LGC_EPI_ADAM = 3 } lgc_epilogue_mode;
+typedef struct {
+  int32_t mode;
+  float a0, a1, scale, beta;
+  float* y;
+  float* acc;
+  const float* xrow;
+  const float* addend;
+  float* p;
+  float* m;
+  float* v;
+  double lr, beta1, beta2, eps;
+  int64_t step;
+} lgc_spmm_epilogue;
+int lgc_spmm_ex(const lgc_graph_t* graph, int ld, const float* x, const lgc_spmm_epilogue* epilogue,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ get_embedding (src/lightgcn.py:91-99)
  * out = sum_{l=0..K} alpha_l A_hat^l x0, evaluated like the reference as a running sum but

@@ -1,0 +1,108 @@
+"""Multi-rank host logic of the row-partitioned training step on CPU (`gloo`, world_size 2 and 3;
+SURVEY.md 8(e)): partition, source renumbering, all-gather / all-reduce plumbing and the Horner
+backward, with a torch restatement of the kernels as the backend (tests/_cpu_backend.py).
+The checker is the oracle's single-process reference step (`oracle.port.train_step`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LR, DECAY, DIM, LAYERS, BATCH = 0.005, 1e-4, 16, 3, 64
+
+
+def _inputs():
+    from gnn_ecommerce_b200 import synth
+    from oracle import port
+    g = synth.make_graph(600, 90, 4000, seed=21)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    torch.manual_seed(5)
+    init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, DIM))
+    pl = synth.purchase_lists(g)
+    rng = np.random.default_rng(6)
+    triples = [tuple(torch.from_numpy(x) for x in synth.sample_triples(pl, BATCH, g.n_users, g.n_items, rng))
+               for _ in range(2)]
+    return g, ei, ew, init, triples
+
+
+def _reference():
+    from oracle import port
+    g, ei, ew, init, triples = _inputs()
+    model = port.PortLightGCN(g.num_nodes, DIM, LAYERS)
+    with torch.no_grad():
+        model.embedding.weight.copy_(init)
+    opt = torch.optim.Adam(model.parameters(), LR)
+    losses = [port.train_step(model, opt, ei, ew, *t, DECAY) for t in triples]
+    with torch.no_grad():
+        emb = model.get_embedding(ei, ew)
+    return np.array(losses), model.embedding.weight.detach().clone(), emb
+
+
+def _worker(rank, world, port_no, out):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _cpu_backend import CpuCheckBackend
+    from gnn_ecommerce_b200.sharded import ShardedBPRTrainer
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
+    g, ei, ew, init, triples = _inputs()
+    tr = ShardedBPRTrainer(ei, ew, g.num_nodes, DIM, LAYERS, init, lr=LR, backend=CpuCheckBackend(), ld=DIM)
+    assert sum(tr.part.hi(r) - tr.part.lo(r) for r in range(world)) == g.num_nodes
+    losses = [tr.step(*t, DECAY).numpy() for t in triples]
+    w, emb = tr.weight(), tr.embedding()
+    if rank == 0:
+        torch.save({"losses": np.array(losses), "w": w, "emb": emb, "bounds": tr.part.bounds,
+                    "local_nnz": tr.local_nnz}, out)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_step_matches_reference(world, tmp_path):
+    out = str(tmp_path / "res.pt")
+    port_no = 29500 + (os.getpid() % 2000) + world
+    if world == 1:
+        _worker(0, 1, port_no, out)
+    else:
+        mp.spawn(_worker, args=(world, port_no, out), nprocs=world, join=True)
+    got = torch.load(out, weights_only=False)
+    want_losses, want_w, want_emb = _reference()
+    assert np.allclose(got["losses"], want_losses, rtol=1e-5, atol=0)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    assert rel(got["w"], want_w) < 5e-4          # two Adam steps amplify last-bit gradient noise
+    assert float((got["w"] - want_w).abs().median()) < 1e-7
+    assert rel(got["emb"], want_emb) < 5e-4
+    b = got["bounds"]
+    assert b[0] == 0 and b[-1] == want_w.shape[0] and np.all(np.diff(b) >= 0)
+
+
+def test_row_partition_balances_cost_and_renumbers():
+    from gnn_ecommerce_b200.sharded import ROW_COST, RowPartition
+    rng = np.random.default_rng(0)
+    deg = np.concatenate([rng.integers(1, 6, 5000), rng.integers(50, 4000, 120)])      # users | hub items
+    part = RowPartition(deg, 4)
+    cost = np.array([(deg[part.lo(r):part.hi(r)] + ROW_COST).sum() for r in range(4)])
+    assert cost.max() / cost.mean() < 1.25
+    ids = torch.from_numpy(rng.integers(0, len(deg), 1000))
+    pid = part.padded_id(ids)
+    own = part.owner(ids)
+    assert torch.all(own == pid // part.max_rows)
+    lo = torch.as_tensor(part.bounds[:-1])[own]
+    assert torch.all(pid - own * part.max_rows == ids - lo)
+    table = torch.arange(4 * part.max_rows).float()[:, None]
+    assert torch.equal(part.unpad(table)[ids, 0], pid.float())
+
+
+def test_shard_users_covers_everyone():
+    from gnn_ecommerce_b200.sharded import shard_users
+    for n, w in [(10, 3), (1_600_000, 8), (5, 8)]:
+        spans = [shard_users(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
