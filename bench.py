@@ -231,8 +231,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gnn_ecommerce_b200 import FusedBPRTrainer, LightGCN, _capi, scoring
+    from gnn_ecommerce_b200 import FusedBPRTrainer, LightGCN, _capi
     from gnn_ecommerce_b200.graph import padded_dim
+    from gnn_ecommerce_b200.sharded import ShardedBPRTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,14 +254,41 @@ def main():
 
     ei = torch.from_numpy(g.edge_index()).to(dev)
     ew = torch.from_numpy(g.edge_weight()).to(dev)
-    model = LightGCN(g.num_nodes, dim, layers)
-    with torch.no_grad():
-        model.embedding.weight.copy_(torch.from_numpy(init))
-    model = model.to(dev)
-    trainer = FusedBPRTrainer(model, lr=LR)
-    graph = model.graph(ei, ew)
+    model, graph = None, None
+    if world == 1:
+        # N = 1: the drop-in module + fused single-GPU step
+        model = LightGCN(g.num_nodes, dim, layers)
+        with torch.no_grad():
+            model.embedding.weight.copy_(torch.from_numpy(init))
+        model = model.to(dev)
+        trainer = FusedBPRTrainer(model, lr=LR)
+        graph = model.graph(ei, ew)
+
+        def step(u, p, n):
+            return trainer.step(ei, ew, u, p, n, DECAY)
+
+        def embedding():
+            from gnn_ecommerce_b200 import ops
+            with torch.no_grad():
+                return ops.full_rows(model.get_embedding(ei, ew))
+    else:
+        # N > 1: destination rows partitioned over the ranks, per-layer NCCL all-gather of the
+        # shards, one small all-reduce of the <= 3*batch loss rows; the SAME
+        # graph is split, so total work is fixed: strong scaling
+        trainer = ShardedBPRTrainer(ei, ew, g.num_nodes, dim, layers, torch.from_numpy(init), lr=LR)
+
+        def step(u, p, n):
+            return trainer.step(u, p, n, DECAY)
+
+        def embedding():
+            return trainer.embedding().contiguous()
+
     if args.only_scoring:
-        print(json.dumps({"scoring": bench_scoring(model, ei, ew, g, dev, args, pk)}), flush=True)
+        sc = bench_scoring(embedding(), g, dev, args, pk, dim, world, rank)
+        if rank == 0:
+            print(json.dumps({"scoring": sc}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return 0
     dev_triples = [tuple(torch.from_numpy(x).to(dev) for x in t) for t in triples]
     pin_triples = [tuple(torch.from_numpy(x).pin_memory() for x in t) for t in triples]
@@ -270,58 +298,65 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     # ---- device-resident timing: W warm-up + exactly K timed steps (inputs: 1 GB+ of tables,
     # far larger than the 126 MB L2, so no flush is needed between iterations)
     for i in range(args.warmup):
-        trainer.step(ei, ew, *dev_triples[i], DECAY)
+        step(*dev_triples[i])
     barrier()
     launches0 = lib.lgc_launch_count()
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         beg.record()
         for i in range(args.steps):
-            loss3 = trainer.step(ei, ew, *dev_triples[args.warmup + i], DECAY)
+            loss3 = step(*dev_triples[args.warmup + i])
         end.record()
         barrier()
     launches = lib.lgc_launch_count() - launches0
-    ms_total = beg.elapsed_time(end)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = max_over_ranks(beg.elapsed_time(end))
     ms_step = ms_total / args.steps
     last_losses = [float(x) for x in loss3.cpu().tolist()]
-    gedges = nnz * 2 * layers * args.steps * world / (ms_total * 1e-3) / 1e9
+    gedges = nnz * 2 * layers * args.steps / (ms_total * 1e-3) / 1e9
 
     # ---- end to end through the public API: pinned host triples -> H2D, losses -> D2H per step
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         u, p, n = (x.to(dev, non_blocking=True) for x in pin_triples[args.warmup + i])
-        host_losses = trainer.step(ei, ew, u, p, n, DECAY).cpu()
+        host_losses = step(u, p, n).cpu()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_gedges = nnz * 2 * layers * args.steps * world / e2e_s / 1e9
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_gedges = nnz * 2 * layers * args.steps / e2e_s / 1e9
 
     # ---- per-kernel-class durations (CUDA events on the launching stream) over K more steps
     n_tags = 24
     ms_arr, cnt_arr = (C.c_double * n_tags)(), (C.c_longlong * n_tags)()
     lib.lgc_profile_enable(1)
     for i in range(args.steps):
-        trainer.step(ei, ew, *dev_triples[args.warmup + i], DECAY)
+        step(*dev_triples[args.warmup + i])
     torch.cuda.synchronize()
     lib.lgc_profile_read(ms_arr, cnt_arr, n_tags)
     lib.lgc_profile_enable(0)
-    prof = {t: (ms_arr[t], cnt_arr[t]) for t in range(n_tags) if cnt_arr[t]}
     light_ms = sum(ms_arr[t] for t in range(0, 4))
     light_cnt = sum(cnt_arr[t] for t in range(0, 4))
     heavy_ms = sum(ms_arr[t] for t in range(4, 8))
     finish_ms = sum(ms_arr[t] for t in range(8, 12))
     kernel_ms_total = sum(ms_arr)
+
+    # ---- scoring (c4): all users x all items, top-20, user-sharded when N > 1
+    score = None
+    if not args.no_scoring:
+        try:
+            score = bench_scoring(embedding(), g, dev, args, pk, dim, world, rank)
+        except Exception as e:  # a missing kernel must not hide the training number
+            log(f"[bench] scoring failed: {e!r}")
+            score = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -329,39 +364,37 @@ def main():
         return 0
 
     alg = algorithmic_bytes(g, ld, layers, nnz)
-    lk = light_kernel_bytes(g, graph, ld)
     light_avg_ms = light_ms / max(light_cnt, 1)
-    achieved = lk["bytes_per_launch"] / (light_avg_ms * 1e-3) / 1e9
-    traffic = None
-    prof_json = os.path.join(ROOT, "profiles", "ncu_light_traffic.json")
-    if os.path.exists(prof_json):
-        try:
-            traffic = float(json.load(open(prof_json))["dram_bytes_per_launch"])
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_spmm_light", "achieved": achieved, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-                "peak_source": pk["source"], "kernel_ms": light_avg_ms,
-                "kernel_share_of_step": light_ms / max(kernel_ms_total, 1e-9),
-                "algorithmic_bytes_per_launch": lk["bytes_per_launch"],
-                "step_algorithmic_bytes": alg["step"],
-                "step_achieved_gbs": alg["step"] / (ms_step * 1e-3) / 1e9,
-                "step_frac": alg["step"] / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
-                "class_ms_per_step": {"light": light_ms / args.steps, "heavy": heavy_ms / args.steps,
-                                      "finish": finish_ms / args.steps,
-                                      "bpr": ms_arr[12] / args.steps}}
-
-    # ---- scoring (c4): all users x all items, top-20, user table resident
-    score = None
-    if not args.no_scoring:
-        try:
-            score = bench_scoring(model, ei, ew, g, dev, args, pk)
-        except Exception as e:  # a missing kernel must not hide the training number
-            log(f"[bench] scoring failed: {e!r}")
-            score = {"error": repr(e)}
+    class_ms = {"light": light_ms / args.steps, "heavy": heavy_ms / args.steps, "finish": finish_ms / args.steps,
+                "bpr": ms_arr[12] / args.steps}
+    step_gbs = alg["step"] / (ms_step * 1e-3) / 1e9
+    if world == 1:
+        lk = light_kernel_bytes(g, graph, ld)
+        achieved = lk["bytes_per_launch"] / (light_avg_ms * 1e-3) / 1e9
+        traffic = None
+        prof_json = os.path.join(ROOT, "profiles", "ncu_light_traffic.json")
+        if os.path.exists(prof_json):
+            try:
+                traffic = float(json.load(open(prof_json))["dram_bytes_per_launch"])
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_spmm_light", "achieved": achieved, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                    "peak_source": pk["source"], "kernel_ms": light_avg_ms,
+                    "kernel_share_of_step": light_ms / max(kernel_ms_total, 1e-9),
+                    "algorithmic_bytes_per_launch": lk["bytes_per_launch"],
+                    "step_algorithmic_bytes": alg["step"], "step_achieved_gbs": step_gbs,
+                    "step_frac": step_gbs / pk["hbm_gbs"], "class_ms_per_step": class_ms}
+    else:
+        # whole step against N x the HBM peak (the all-gathers add NVLink time on top of it)
+        roofline = {"bound": "hbm", "kernel": "whole step, all ranks", "achieved": step_gbs,
+                    "peak": pk["hbm_gbs"] * world, "unit": "GB/s", "frac": step_gbs / (pk["hbm_gbs"] * world),
+                    "traffic": None, "peak_source": pk["source"], "step_algorithmic_bytes": alg["step"],
+                    "class_ms_per_step_rank0": class_ms,
+                    "allgather_bytes_per_step_per_gpu": (2 * layers - 1) * trainer.n_cols * ld * 4 * (world - 1) // world}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         dt, cores = cpu_full_step(g, dim, layers, init, triples[0])
         cpu = {"value": nnz * 2 * layers / dt / 1e9, "unit": "GEdges/s", "cores": cores, "kind": "port",
                "sample": f"1 full training step (K={layers} fwd + BPR + bwd + dense Adam) at {args.config} "
@@ -372,11 +405,13 @@ def main():
     line = {
         "metric": "lgconv_gedges_per_s", "value": gedges, "unit": "GEdges/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: LightGCN K={layers} d={dim}, N={g.num_nodes}, nnz={nnz}, "
                                f"batch={BATCH}, full training step (fwd+BPR+bwd+Adam)",
                    "l2": "inputs (>=1 GB of tables per step) exceed the 126 MB L2; no flush",
-                   "steps_per_epoch": steps_per_epoch},
+                   "steps_per_epoch": steps_per_epoch,
+                   "parallelism": "single GPU" if world == 1 else
+                                  f"destination rows partitioned over {world} GPUs, NCCL all-gather per layer"},
         "epoch_s": ms_step * steps_per_epoch * 1e-3,
         "losses_last_step": last_losses,
         "e2e": {"value": e2e_gedges, "unit": "GEdges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
@@ -394,25 +429,28 @@ def main():
     return 0
 
 
-def bench_scoring(model, ei, ew, g, dev, args, pk):
+def bench_scoring(rows, g, dev, args, pk, dim, world=1, rank=0):
+    """c4: top-20 of all users x all items from the final embedding table `rows` ([N, >=dim]);
+    users are sharded over the ranks (no communication), time = max over ranks."""
     import torch
-    from gnn_ecommerce_b200 import _capi, ops, scoring, synth
+    import torch.distributed as dist
+    from gnn_ecommerce_b200 import _capi, scoring, synth
+    from gnn_ecommerce_b200.sharded import shard_users
     k = 20
-    with torch.no_grad():
-        emb = model.get_embedding(ei, ew)
-    rows = ops.full_rows(emb)
     n_score = args.score_users or g.n_users
-    users = torch.arange(n_score, device=dev)
-    ptr, items = synth.seen_lists(g, np.arange(n_score))
+    u0, u1 = shard_users(n_score, world, rank)
+    users = torch.arange(u0, u1, device=dev)
+    ptr, items = synth.seen_lists(g, np.arange(u0, u1))
     seen = scoring.SeenLists.from_numpy(ptr, items, dev)
     user_t, item_t = rows[:g.n_users], rows[g.n_users:]
 
     def run():
-        return scoring.score_topk(user_t, item_t, users, seen.ptr, seen.items, k,
-                                  d=model.embedding_dim, return_stats=True)
+        return scoring.score_topk(user_t, item_t, users, seen.ptr, seen.items, k, d=dim, return_stats=True)
     for _ in range(2):
         run()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
     rep_ms = []
@@ -435,16 +473,22 @@ def bench_scoring(model, ei, ew, g, dev, args, pk):
              21: "exhaustive"}
     class_ms = {names[t]: ms_arr[t] for t in names}
     gemm_ms = max(ms_arr[17], 1e-9)
-    flops = 2.0 * n_score * g.n_items * model.embedding_dim
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    flops_local = 2.0 * (u1 - u0) * g.n_items * dim
+    flops = 2.0 * n_score * g.n_items * dim
     tf = flops / (ms * 1e-3) / 1e12
     st = stats.cpu().tolist()
     return {"metric": "top20_users_per_s", "value": n_score / (ms * 1e-3), "unit": "users/s",
-            "users": n_score, "items": g.n_items, "k": k, "ms": ms,
-            "roofline": {"bound": "tensor", "kernel": "k_score_gemm", "achieved": flops / (gemm_ms * 1e-3) / 1e12,
+            "users": n_score, "items": g.n_items, "k": k, "ms": ms, "n_gpus": world,
+            "roofline": {"bound": "tensor", "kernel": "k_score_gemm",
+                         "achieved": flops_local / (gemm_ms * 1e-3) / 1e12,
                          "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": flops / (gemm_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                         "frac": flops_local / (gemm_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None,
                          "peak_source": pk["source"], "kernel_ms": gemm_ms,
-                         "whole_call_tflops": tf, "whole_call_frac": tf / pk["bf16_tflops"]},
+                         "whole_call_tflops": tf, "whole_call_frac": tf / (pk["bf16_tflops"] * world)},
             "class_ms": class_ms, "rep_ms": rep_ms,
             "fallback_users": st[0], "candidate_groups": st[1]}
 

@@ -379,62 +379,68 @@ k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks, const int32_t* __r
   constexpr int U = (L >= 8) ? 8 : L;  // gathers in flight per stream and unrolled step
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, sl = lane % L;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (warp >= num_chunks) return;
-  const int4 c = chunks[warp];
-  const int row = c.x, beg = c.y, end = c.z, slot = c.w;
+  // persistent: the grid is sized to the resident warps; chunk c goes to warp c mod #warps, so
+  // every warp gets the same mix of long (hub) and short chunks and no CTA slot idles on a tail
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int c_idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c_idx < num_chunks; c_idx += n_warps) {
+    const int4 c = chunks[c_idx];
+    const int row = c.x, beg = c.y, end = c.z, slot = c.w;
 
-  float4 acc[V];
+    float4 acc[V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int base = beg; base < end; base += 32) {
-    int my_s = 0; float my_w = 0.f;
-    if (base + lane < end) { my_s = src[base + lane]; my_w = w[base + lane]; }
-    const int n = min(32, end - base);
-    // stream `sub` takes entries sub, sub+RPW, ... of this block of 32
+    // (source, weight) of the next 32 edges are requested before the current 32 are gathered
+    int nxt_s = 0; float nxt_w = 0.f;
+    if (beg + lane < end) { nxt_s = src[beg + lane]; nxt_w = w[beg + lane]; }
+    for (int base = beg; base < end; base += 32) {
+      const int my_s = nxt_s; const float my_w = nxt_w;
+      if (base + 32 + lane < end) { nxt_s = src[base + 32 + lane]; nxt_w = w[base + 32 + lane]; }
+      const int n = min(32, end - base);
+      // stream `sub` takes entries sub, sub+RPW, ... of this block of 32
 #pragma unroll
-    for (int t0 = 0; t0 < L; t0 += U) {
-      float ww[U]; float4 xv[U][V];
+      for (int t0 = 0; t0 < L; t0 += U) {
+        float ww[U]; float4 xv[U][V];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = (t0 + u) * RPW + sub;
-        const int s = __shfl_sync(0xffffffffu, my_s, idx);
-        ww[u] = __shfl_sync(0xffffffffu, my_w, idx);
-        if (idx < n) {
-          const float* xr = x + (size_t)s * LD + 4 * sl;
+        for (int u = 0; u < U; ++u) {
+          const int idx = (t0 + u) * RPW + sub;
+          const int s = __shfl_sync(0xffffffffu, my_s, idx);
+          ww[u] = __shfl_sync(0xffffffffu, my_w, idx);
+          if (idx < n) {
+            const float* xr = x + (size_t)s * LD + 4 * sl;
 #pragma unroll
-          for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+            for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+          }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if ((t0 + u) * RPW + sub < n) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = fma4(ww[u], xv[u][v], acc[v]);
+          }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if ((t0 + u) * RPW + sub < n) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = fma4(ww[u], xv[u][v], acc[v]);
-        }
     }
-  }
-  // combine the RPW edge streams (fixed order: deterministic)
+    // combine the RPW edge streams (fixed order: deterministic)
 #pragma unroll
-  for (int o = L; o < 32; o <<= 1) {
+    for (int o = L; o < 32; o <<= 1) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
-      acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
-      acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
-      acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+      for (int v = 0; v < V; ++v) {
+        acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+        acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+        acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+        acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+      }
     }
-  }
-  if (sub != 0) return;
-  if (slot >= 0) {
-    float* pr = partials + (size_t)slot * LD + 4 * sl;
+    if (sub != 0) continue;
+    if (slot >= 0) {
+      float* pr = partials + (size_t)slot * LD + 4 * sl;
 #pragma unroll
-    for (int v = 0; v < V; ++v) st_f4(pr + 4 * L * v, acc[v]);
-  } else {
-    const size_t off = (size_t)row * LD + 4 * sl;
+      for (int v = 0; v < V; ++v) st_f4(pr + 4 * L * v, acc[v]);
+    } else {
+      const size_t off = (size_t)row * LD + 4 * sl;
 #pragma unroll
-    for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+      for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+    }
   }
 }
 
@@ -496,7 +502,7 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   }
   LGC_LAUNCH_CHECK();
   if (g->num_chunks > 0) {
-    const int grid_heavy = (int)ceil_div(g->num_chunks, wpb);
+    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, wpb), kNumSMs * ((V == 1) ? 3 : 2));
     {
       ProfScope ps(PROF_HEAVY + MODE, st);
       k_spmm_heavy<L, V, MODE><<<grid_heavy, threads, 0, st>>>(g->chunks, (int)g->num_chunks, g->src,

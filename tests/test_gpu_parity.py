@@ -326,3 +326,34 @@ def test_c2_full_size_against_reference_gpu_path():
     assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs))
     comb = conv(2.0 * x - 0.5 * y, ei, ew)
     assert rel(comb.cpu(), (2.0 * ax - 0.5 * ay).cpu()) < 1e-5
+
+
+# --------------------------------------------------------------------------- sharded driver, 1 rank
+@pytest.mark.parametrize("dim,layers", [(64, 3), (90, 5), (16, 1)])
+def test_sharded_trainer_single_rank_equals_fused(dim, layers):
+    """The row-partitioned driver (lgc_graph_build_rect + lgc_spmm_ex + compact BPR rows) with one
+    rank must reproduce the fused single-GPU step; multi-rank orchestration is covered on CPU
+    (tests/test_sharded_cpu.py) and on 2+ GPUs by bench.py."""
+    from gnn_ecommerce_b200 import FusedBPRTrainer
+    from gnn_ecommerce_b200.sharded import ShardedBPRTrainer
+    g = synth.make_graph(3000, 500, 40_000, seed=13)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    torch.manual_seed(7)
+    init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, dim))
+    mf = _model(g.num_nodes, dim, layers, init.numpy())
+    fused = FusedBPRTrainer(mf, lr=LR)
+    sharded = ShardedBPRTrainer(eig, ewg, g.num_nodes, dim, layers, init, lr=LR)
+    pl = synth.purchase_lists(g)
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+        u, p, n = (torch.from_numpy(x).to(DEV) for x in synth.sample_triples(pl, 200, g.n_users, g.n_items, rng))
+        a = fused.step(eig, ewg, u, p, n, DECAY).cpu().numpy()
+        b = sharded.step(u, p, n, DECAY).cpu().numpy()
+        assert np.allclose(a, b, rtol=2e-5)
+    wf, ws = mf.embedding.weight.detach().cpu(), sharded.weight().cpu()
+    assert ws.shape == (g.num_nodes, dim)
+    assert rel(ws, wf) < 5e-4 and np.median(np.abs(ws.numpy() - wf.numpy())) < 1e-7
+    with torch.no_grad():
+        ef = mf.get_embedding(eig, ewg).cpu()
+    assert rel(sharded.embedding().cpu(), ef) < 5e-4
