@@ -38,8 +38,19 @@ if ROOT not in sys.path:
 BATCH, LR, DECAY = 1024, 0.005, 1e-4       # src/train_lightgcn.py:47-53
 
 
+_REAL_STDOUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def peaks():
@@ -208,7 +219,7 @@ def reference_arm(args):
                              "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "GEdges/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -224,8 +235,16 @@ def main():
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--only-scoring", action="store_true", help="skip the training-step timing (dev aid)")
     ap.add_argument("--score-users", type=int, default=0, help="0 = all users (c4)")
+    ap.add_argument("--shard-mode", default="auto", choices=["auto", "bipartite", "rows"],
+                    help="N > 1: how the training step is sharded")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner
+    # when NCCL_DEBUG is set) is sent to stderr; emit() writes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -233,7 +252,7 @@ def main():
     import torch.distributed as dist
     from gnn_ecommerce_b200 import FusedBPRTrainer, LightGCN, _capi
     from gnn_ecommerce_b200.graph import padded_dim
-    from gnn_ecommerce_b200.sharded import ShardedBPRTrainer
+    from gnn_ecommerce_b200.sharded import make_sharded_trainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,6 +262,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
     pk = peaks()
@@ -272,10 +293,13 @@ def main():
             with torch.no_grad():
                 return ops.full_rows(model.get_embedding(ei, ew))
     else:
-        # N > 1: destination rows partitioned over the ranks, per-layer NCCL all-gather of the
-        # shards, one small all-reduce of the <= 3*batch loss rows; the SAME
-        # graph is split, so total work is fixed: strong scaling
-        trainer = ShardedBPRTrainer(ei, ew, g.num_nodes, dim, layers, torch.from_numpy(init), lr=LR)
+        # N > 1: the SAME graph is split over the ranks (strong scaling). Default "auto" = bipartite-
+        # aware sharding (users partitioned, item table replicated, one all-reduce of the item
+        # partial sums per layer); "rows" = destination rows partitioned + all-gather per layer
+        # (SURVEY.md 8(e)). Both exchange the <= 3*batch loss rows with one small all-reduce.
+        trainer = make_sharded_trainer(ei, ew, g.num_nodes, dim, layers, torch.from_numpy(init),
+                                       mode=args.shard_mode, lr=LR)
+        shard_kind = type(trainer).__name__
 
         def step(u, p, n):
             return trainer.step(u, p, n, DECAY)
@@ -286,7 +310,7 @@ def main():
     if args.only_scoring:
         sc = bench_scoring(embedding(), g, dev, args, pk, dim, world, rank)
         if rank == 0:
-            print(json.dumps({"scoring": sc}), flush=True)
+            emit({"scoring": sc})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -386,12 +410,18 @@ def main():
                     "step_algorithmic_bytes": alg["step"], "step_achieved_gbs": step_gbs,
                     "step_frac": step_gbs / pk["hbm_gbs"], "class_ms_per_step": class_ms}
     else:
-        # whole step against N x the HBM peak (the all-gathers add NVLink time on top of it)
+        # whole step against N x the HBM peak (the collectives add NVLink time on top of it)
+        if shard_kind == "BipartiteShardedTrainer":
+            comm = 2 * layers * g.n_items * ld * 4 * 2 * (world - 1) // world     # ring all-reduce volume
+            par = (f"users partitioned over {world} GPUs, item table replicated, NCCL all-reduce of the item "
+                   f"partial sums per layer")
+        else:
+            comm = (2 * layers - 1) * trainer.n_cols * ld * 4 * (world - 1) // world
+            par = f"destination rows partitioned over {world} GPUs, NCCL all-gather per layer"
         roofline = {"bound": "hbm", "kernel": "whole step, all ranks", "achieved": step_gbs,
                     "peak": pk["hbm_gbs"] * world, "unit": "GB/s", "frac": step_gbs / (pk["hbm_gbs"] * world),
                     "traffic": None, "peak_source": pk["source"], "step_algorithmic_bytes": alg["step"],
-                    "class_ms_per_step_rank0": class_ms,
-                    "allgather_bytes_per_step_per_gpu": (2 * layers - 1) * trainer.n_cols * ld * 4 * (world - 1) // world}
+                    "class_ms_per_step_rank0": class_ms, "nvlink_bytes_per_step_per_gpu": comm}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -410,8 +440,7 @@ def main():
                                f"batch={BATCH}, full training step (fwd+BPR+bwd+Adam)",
                    "l2": "inputs (>=1 GB of tables per step) exceed the 126 MB L2; no flush",
                    "steps_per_epoch": steps_per_epoch,
-                   "parallelism": "single GPU" if world == 1 else
-                                  f"destination rows partitioned over {world} GPUs, NCCL all-gather per layer"},
+                   "parallelism": "single GPU" if world == 1 else par},
         "epoch_s": ms_step * steps_per_epoch * 1e-3,
         "losses_last_step": last_losses,
         "e2e": {"value": e2e_gedges, "unit": "GEdges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
@@ -423,7 +452,7 @@ def main():
         "cpu_baseline": cpu,
         "scoring": score,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "lgc_bpr_workspace_bytes": (c_sz, [c_i64]),
     "lgc_bpr_loss_grad": (C.c_int, [c_i64, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f64, c_f32,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lgc_scatter_add_rows": (C.c_int, [c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "lgc_adam_step": (C.c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_f64, c_f64, c_f64, c_f64, c_i64, c_vp]),
     "lgc_train_step_workspace_bytes": (c_sz, [c_vp, C.c_int, C.c_int, c_i64]),
     "lgc_train_workspace_init": (C.c_int, [c_vp, C.c_int, C.c_int, c_i64, c_vp, c_sz, c_vp]),

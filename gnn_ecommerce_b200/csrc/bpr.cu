@@ -120,6 +120,48 @@ __global__ void k_bpr_reduce(const float* __restrict__ per_triple, int64_t batch
   }
 }
 
+// table[idx[j]] += rows[j] for j < n with duplicates summed in input order (deterministic: the
+// multi-GPU step keeps REPLICATED item tables that must stay bit-identical on every rank, which
+// atomics cannot guarantee). One warp per input row j: it is the leader of its index if no
+// earlier row carries the same index; a leader adds all rows of that index, in order.
+// idx < 0 entries are skipped (rows that belong to another rank).
+__global__ void k_scatter_add_rows(int n, int ld, const int64_t* __restrict__ idx, const float* __restrict__ rows,
+                                   float* __restrict__ table) {
+  const int j = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const int64_t me = idx[j];
+  if (me < 0) return;
+  bool dup = false;
+  for (int q = lane; q < j; q += 32) dup |= (idx[q] == me);
+  if (__any_sync(0xffffffffu, dup)) return;
+  const int vec = ld / 4;
+  float4 acc[kMaxVecPerLane];
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = j; base < n; base += 32) {
+    const int q = base + lane;
+    unsigned hit = __ballot_sync(0xffffffffu, q < n && idx[q] == me);
+    while (hit) {
+      const int r = base + __ffs(hit) - 1;
+      hit &= hit - 1;
+#pragma unroll
+      for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (c < vec) acc[k] = add4(acc[k], ldg_f4(rows + (size_t)r * ld + 4 * c));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < vec) {
+      float* dst = table + (size_t)me * ld + 4 * c;
+      st_f4(dst, add4(ld_f4(dst), acc[k]));
+    }
+  }
+}
+
 __global__ void k_adam(int64_t n4, float4* __restrict__ p, const float4* __restrict__ g,
                        float4* __restrict__ m, float4* __restrict__ v, AdamScalars s) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
@@ -168,6 +210,17 @@ extern "C" int lgc_pair_scores(int ld, const float* out, const int64_t* pairs, i
   if (n_pairs == 0) return LGC_OK;
   k_pair_scores<<<(int)ceil_div(n_pairs * 32, 256), 256, 0, (cudaStream_t)stream>>>(out, ld, pairs,
                                                                                      n_pairs, score);
+  LGC_LAUNCH_CHECK();
+  return LGC_OK;
+}
+
+extern "C" int lgc_scatter_add_rows(int64_t n, int ld, const int64_t* idx, const float* rows, float* table,
+                                    void* stream) {
+  LGC_REQUIRE(idx && rows && table, "null argument");
+  LGC_REQUIRE(ld > 0 && ld % 4 == 0 && ld <= 128 * kMaxVecPerLane, "unsupported ld");
+  LGC_REQUIRE(n >= 0 && n < (1 << 24), "row count out of range");
+  if (n == 0) return LGC_OK;
+  k_scatter_add_rows<<<(int)ceil_div(n * 32, 256), 256, 0, (cudaStream_t)stream>>>((int)n, ld, idx, rows, table);
   LGC_LAUNCH_CHECK();
   return LGC_OK;
 }

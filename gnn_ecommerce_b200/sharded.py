@@ -116,6 +116,18 @@ class CudaBackend:
             rc = self._lib.lgc_spmm_ex(handle, ld, _ptr(x), C.byref(e), _ptr(ws), ws.numel(), _stream())
         self._capi.check(rc, "lgc_spmm_ex")
 
+    def scatter_add(self, table: Tensor, idx: Tensor, rows: Tensor) -> None:
+        """table[idx[j]] += rows[j], duplicates in input order (deterministic); idx < 0 skipped."""
+        from .graph import _ptr, _stream
+        with torch.cuda.device(table.device):
+            rc = self._lib.lgc_scatter_add_rows(idx.numel(), table.stride(0), _ptr(idx.contiguous()),
+                                                _ptr(rows.contiguous()), _ptr(table), _stream())
+        self._capi.check(rc, "lgc_scatter_add_rows")
+
+    def adam_step(self, p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, betas, eps: float, step: int):
+        from . import ops
+        ops.adam_step(p, g.contiguous(), m, v, lr, betas, eps, step)
+
     def bpr(self, outc: Tensor, e0c: Tensor, batch: int, decay: float, alpha0: float):
         """BPR + L2 on the compact `[3*batch, ld]` row tables (users | pos | neg)."""
         from . import ops
@@ -221,19 +233,19 @@ class ShardedBPRTrainer:
         self.propagate()
 
         # ---- the <= 3*batch needed rows of out / E0: owners contribute, one small all-reduce
+        # (fixed shapes, no host synchronisation: rows of other ranks are masked to zero)
         ids = torch.cat([users, pos, neg]).to(device=self.dev, dtype=torch.int64)
         mine = (ids >= self.lo) & (ids < self.hi)
-        loc = (ids - self.lo)[mine]
-        rows = torch.zeros(2, 3 * batch, ld, dtype=torch.float32, device=self.dev)
-        rows[0, mine] = self.out[loc]
-        rows[1, mine] = self.e0[loc]
+        loc = torch.where(mine, ids - self.lo, -1)
+        locc = loc.clamp_min(0)
+        rows = torch.stack([self.out[locc], self.e0[locc]]) * mine[None, :, None]
         self._all_reduce(rows)
         loss3, gc, zc = b.bpr(rows[0], rows[1], batch, float(decay), a[0])
 
         # ---- gradient rows: dL/d out for everybody (gather source of the backward), Z for owners
         pid = self.part.padded_id(ids)
-        self.gfull.index_add_(0, pid, gc)
-        self.z.index_add_(0, loc, zc[mine])
+        b.scatter_add(self.gfull, pid, gc)
+        b.scatter_add(self.z, loc, zc)
         g_local = self.gfull[self.rank * self.max_rows: (self.rank + 1) * self.max_rows]
 
         # ---- backward (Horner on the symmetric operator) + Adam on the owned rows
@@ -246,7 +258,7 @@ class ShardedBPRTrainer:
         b.spmm_ex(self.handle, ld, cur, self.ws, 3, addend=self.z, scale=scale, p=self.e0, m=self.m, v=self.v,
                   lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count)
         self.gfull.index_fill_(0, pid, 0.0)
-        self.z.index_fill_(0, loc, 0.0)
+        self.z.index_fill_(0, locc, 0.0)
         return loss3
 
     # ------------------------------------------------------------------ views for callers / tests
@@ -262,3 +274,187 @@ def shard_users(n_users: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous user range of `rank` for user-sharded scoring (no communication)."""
     per = (n_users + world - 1) // world
     return min(n_users, rank * per), min(n_users, (rank + 1) * per)
+
+
+# --------------------------------------------------------------------------------- bipartite-aware
+def bipartite_split(edge_index: Tensor) -> Optional[int]:
+    """`s` such that every edge joins a node < s (a user) with a node >= s (an item) -- the layout
+    `df_to_graph` produces (items offset by n_users, reference `src/utils_v2.py:128`) -- else None."""
+    if edge_index.numel() == 0:
+        return None
+    s = int(torch.minimum(edge_index.max(dim=0).values.min(), edge_index.max()).item())
+    lo_side = edge_index < s
+    return s if bool((lo_side[0] != lo_side[1]).all()) and s > 0 else None
+
+
+class BipartiteShardedTrainer:
+    """Bipartite-aware sharding of the same step (~30x less traffic than the
+    all-gather of whole tables): USERS are partitioned over the ranks (balanced by in-degree + 4),
+    the small ITEM table is replicated. Per layer a rank computes its users' rows from the replicated
+    item table (fused epilogue, no communication) and the PARTIAL sums of every item row over its
+    own users; one all-reduce of the `[n_items, ld]` partials completes the item rows, whose
+    (tiny, replicated) epilogue every rank applies identically. Item-row sums are therefore reduced
+    in a different order than on one GPU: equal within fp32 tolerance, not bit-exact."""
+
+    def __init__(self, edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int, embedding_dim: int,
+                 num_layers: int, init_weight: Tensor, n_users: int, lr: float = 0.005, betas=(0.9, 0.999),
+                 eps: float = 1e-8, alpha: Optional[Sequence[float]] = None, group=None, backend=None,
+                 ld: Optional[int] = None):
+        assert num_layers >= 1
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.backend = backend if backend is not None else CudaBackend()
+        self.dev = edge_index.device
+        self.num_nodes, self.dim, self.layers = int(num_nodes), int(embedding_dim), int(num_layers)
+        self.n_users, self.n_items = int(n_users), int(num_nodes) - int(n_users)
+        if ld is None:
+            from .graph import padded_dim
+            ld = padded_dim(self.dim)
+        self.ld = ld
+        self.alpha = [float(a) for a in (alpha if alpha is not None else [1.0 / (num_layers + 1)] * (num_layers + 1))]
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.step_count = 0
+
+        w_hat, deg, sym = self.backend.global_w_hat(edge_index, edge_weight, self.num_nodes)
+        if not sym:
+            raise RuntimeError("the sharded step needs a symmetric graph (backward reuses the operator)")
+        s = self.n_users
+        self.part = RowPartition(deg[:s].cpu().numpy(), self.world)          # users only
+        lo, hi = self.part.lo(self.rank), self.part.hi(self.rank)
+        self.lo, self.hi, self.n_local, self.max_rows = lo, hi, hi - lo, self.part.max_rows
+        src, dst = edge_index[0], edge_index[1]
+        to_user = (dst >= lo) & (dst < hi)                                   # item -> my user
+        to_item = (src >= lo) & (src < hi)                                   # my user -> item
+        self.gu = self.backend.build_rect(src[to_user] - s, dst[to_user] - lo, w_hat[to_user],
+                                          max(self.n_local, 1), self.n_items)
+        self.gi = self.backend.build_rect(src[to_item] - lo, dst[to_item] - s, w_hat[to_item],
+                                          self.n_items, self.max_rows)       # user tables have max_rows rows
+        self.local_nnz = int(to_user.sum().item()) + int(to_item.sum().item())
+        del w_hat, to_user, to_item
+        self.ws_u = self.backend.workspace(self.gu, ld, self.dev)
+        self.ws_i = self.backend.workspace(self.gi, ld, self.dev)
+
+        def table(rows):
+            return torch.zeros(max(rows, 1), ld, dtype=torch.float32, device=self.dev)
+        nu, ni = self.max_rows, self.n_items
+        self.e0_u, self.m_u, self.v_u = table(nu), table(nu), table(nu)
+        self.e0_i, self.m_i, self.v_i = table(ni), table(ni), table(ni)
+        self.e0_u[: self.n_local, : self.dim] = init_weight[lo:hi].to(self.dev)
+        self.e0_i[:, : self.dim] = init_weight[s:].to(self.dev)
+        self.out_u, self.out_i = table(nu), table(ni)
+        self.xu, self.xi = [table(nu), table(nu)], [table(ni), table(ni)]
+        self.part_i = table(ni)                                              # partial item sums
+        self.g_u, self.z_u, self.g_i, self.z_i = table(nu), table(nu), table(ni), table(ni)
+        self.n_cols = self.n_items                                           # rows exchanged per layer
+
+    def __del__(self):
+        for name in ("gu", "gi"):
+            h = getattr(self, name, None)
+            setattr(self, name, None)
+            if h is not None:
+                try:
+                    self.backend.destroy(h)
+                except Exception:
+                    pass
+
+    def _all_reduce(self, t: Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+
+    def _item_rows(self, x_u: Tensor, out: Tensor) -> Tensor:
+        """out = (A_hat x)[items] = all-reduce of every rank's partial sums over its own users."""
+        self.backend.spmm_ex(self.gi, self.ld, x_u, self.ws_i, 0, y=out, scale=1.0)
+        self._all_reduce(out)
+        return out
+
+    # ------------------------------------------------------------------ forward only
+    def propagate(self) -> Tuple[Tensor, Tensor]:
+        b, a, K = self.backend, self.alpha, self.layers
+        cu, ci = self.e0_u, self.e0_i
+        for l in range(1, K + 1):
+            last = l == K
+            nu, ni = self.xu[l & 1], self.xi[l & 1]
+            yi = self._item_rows(cu, self.part_i if last else ni)
+            b.spmm_ex(self.gu, self.ld, ci, self.ws_u, 1 if l == 1 else 2, y=None if last else nu, acc=self.out_u,
+                      xrow=self.e0_u, a0=a[0], a1=a[l])
+            if l == 1:
+                torch.mul(self.e0_i, a[0], out=self.out_i)
+            self.out_i.add_(yi, alpha=a[l])                    # replicated epilogue of the item rows
+            cu, ci = nu, ni
+        return self.out_u, self.out_i
+
+    # ------------------------------------------------------------------ one mini-batch
+    def step(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
+        b, a, K, ld, s = self.backend, self.alpha, self.layers, self.ld, self.n_users
+        batch = users.numel()
+        self.step_count += 1
+        self.propagate()
+
+        users = users.to(device=self.dev, dtype=torch.int64)
+        items = torch.cat([pos, neg]).to(device=self.dev, dtype=torch.int64) - s
+        mine = (users >= self.lo) & (users < self.hi)
+        loc = torch.where(mine, users - self.lo, -1)            # fixed shapes, no host synchronisation
+        locc = loc.clamp_min(0)
+        urows = torch.stack([self.out_u[locc], self.e0_u[locc]]) * mine[None, :, None]
+        self._all_reduce(urows)                              # the batch's user rows; item rows are local
+        outc = torch.cat([urows[0], self.out_i[items]])
+        e0c = torch.cat([urows[1], self.e0_i[items]])
+        loss3, gc, zc = b.bpr(outc, e0c, batch, float(decay), a[0])
+        b.scatter_add(self.g_u, loc, gc[:batch])
+        b.scatter_add(self.z_u, loc, zc[:batch])
+        b.scatter_add(self.g_i, items, gc[batch:])           # replicated: bit-identical on every rank
+        b.scatter_add(self.z_i, items, zc[batch:])
+
+        # ---- backward (Horner on the symmetric operator) + Adam
+        cu, ci, scale = self.g_u, self.g_i, a[K]
+        for l in range(K - 1, 0, -1):                         # h_l = alpha_l G + A h_{l+1}
+            nu, ni = self.xu[l & 1], self.xi[l & 1]
+            yi = self._item_rows(cu, ni)
+            b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=nu, addend=self.g_u, scale=scale, beta=a[l])
+            if scale != 1.0:
+                yi.mul_(scale)
+            yi.add_(self.g_i, alpha=a[l])
+            cu, ci, scale = nu, ni, 1.0
+        yi = self._item_rows(cu, self.part_i)
+        b.spmm_ex(self.gu, ld, ci, self.ws_u, 3, addend=self.z_u, scale=scale, p=self.e0_u, m=self.m_u, v=self.v_u,
+                  lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count)
+        if scale != 1.0:
+            yi.mul_(scale)
+        yi.add_(self.z_i)
+        b.adam_step(self.e0_i, yi, self.m_i, self.v_i, self.lr, self.betas, self.eps, self.step_count)
+        self.g_u.index_fill_(0, locc, 0.0)
+        self.z_u.index_fill_(0, locc, 0.0)
+        self.g_i.index_fill_(0, items, 0.0)
+        self.z_i.index_fill_(0, items, 0.0)
+        return loss3
+
+    # ------------------------------------------------------------------ views for callers / tests
+    def _gather_users(self, shard: Tensor) -> Tensor:
+        full = torch.empty(self.world * self.max_rows, self.ld, dtype=torch.float32, device=self.dev)
+        if self.world == 1:
+            full.copy_(shard)
+        else:
+            dist.all_gather_into_tensor(full, shard, group=self.group)
+        return self.part.unpad(full)
+
+    def weight(self) -> Tensor:
+        return torch.cat([self._gather_users(self.e0_u), self.e0_i])[:, : self.dim]
+
+    def embedding(self) -> Tensor:
+        self.propagate()
+        return torch.cat([self._gather_users(self.out_u), self.out_i])[:, : self.dim]
+
+
+def make_sharded_trainer(edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int, embedding_dim: int,
+                         num_layers: int, init_weight: Tensor, mode: str = "auto", **kw):
+    """`mode`: "bipartite" (users sharded, items replicated + all-reduced), "rows" (destination rows
+    partitioned, all-gather per layer -- works for any symmetric graph) or "auto" (bipartite when the
+    edge list has the users-then-items layout)."""
+    s = bipartite_split(edge_index) if mode in ("auto", "bipartite") else None
+    if mode == "bipartite" and s is None:
+        raise ValueError("edge_index is not bipartite with users numbered before items")
+    if s is not None:
+        return BipartiteShardedTrainer(edge_index, edge_weight, num_nodes, embedding_dim, num_layers, init_weight,
+                                       n_users=s, **kw)
+    return ShardedBPRTrainer(edge_index, edge_weight, num_nodes, embedding_dim, num_layers, init_weight, **kw)

@@ -165,6 +165,11 @@ int lgc_bpr_loss_grad(int64_t num_nodes, int ld, int64_t batch, const int64_t* u
                       double decay, float alpha0, float* grad_out, float* grad_e0, int32_t* touched,
                       float* loss3, void* workspace, size_t workspace_bytes, void* stream);
 
+/* table[idx[j], :] += rows[j, :] for j < n; duplicates are summed in input order (deterministic,
+ * no atomics), entries with idx[j] < 0 are skipped. The multi-GPU step uses it to scatter the
+ * <= 3*batch gradient rows into its (replicated or sharded) tables. rows: [n, ld]. */
+int lgc_scatter_add_rows(int64_t n, int ld, const int64_t* idx, const float* rows, float* table, void* stream);
+
 /* ------------------------------------------------------------------ Adam (src/train_lightgcn.py:58,147)
  * torch.optim.Adam defaults (no weight decay, no amsgrad), dense over `n` contiguous floats,
  * single pass: reads p, g, m, v; writes p, m, v. `step` is the 1-based step count. Hyper-

@@ -17,7 +17,7 @@ class CpuCheckBackend:
         return torch.from_numpy(csr["w_hat_edge"].copy()), torch.from_numpy(csr["count_deg"].copy()), True
 
     def build_rect(self, src, dst, w, n_rows, n_cols):
-        assert int(src.max()) < n_cols and int(dst.max()) < n_rows
+        assert src.numel() == 0 or (int(src.max()) < n_cols and int(dst.max()) < n_rows)
         return {"src": src.clone(), "dst": dst.clone(), "w": w.clone(), "n_rows": n_rows, "n_cols": n_cols}
 
     def destroy(self, handle):
@@ -53,6 +53,19 @@ class CpuCheckBackend:
             v[:n] = v[:n] * torch.tensor(b2, dtype=f) + torch.tensor(1 - b2, dtype=f) * g * g
             denom = v[:n].sqrt() / torch.tensor(math.sqrt(bc2), dtype=f) + torch.tensor(eps, dtype=f)
             p[:n] = p[:n] + torch.tensor(-(lr / bc1), dtype=f) * m[:n] / denom
+
+    def scatter_add(self, table, idx, rows):
+        keep = idx >= 0
+        table.index_add_(0, idx[keep], rows[keep])        # CPU index_add_ is sequential: deterministic
+
+    def adam_step(self, p, g, m, v, lr, betas, eps, step):
+        f = torch.float32
+        b1, b2 = betas
+        bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+        m.copy_(m + torch.tensor(1 - b1, dtype=f) * (g - m))
+        v.copy_(v * torch.tensor(b2, dtype=f) + torch.tensor(1 - b2, dtype=f) * g * g)
+        denom = v.sqrt() / torch.tensor(math.sqrt(bc2), dtype=f) + torch.tensor(eps, dtype=f)
+        p.add_(torch.tensor(-(lr / bc1), dtype=f) * m / denom)
 
     def bpr(self, outc, e0c, batch, decay, alpha0):
         o = outc.clone().requires_grad_(True)

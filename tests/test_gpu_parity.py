@@ -329,13 +329,14 @@ def test_c2_full_size_against_reference_gpu_path():
 
 
 # --------------------------------------------------------------------------- sharded driver, 1 rank
+@pytest.mark.parametrize("mode", ["rows", "bipartite"])
 @pytest.mark.parametrize("dim,layers", [(64, 3), (90, 5), (16, 1)])
-def test_sharded_trainer_single_rank_equals_fused(dim, layers):
+def test_sharded_trainer_single_rank_equals_fused(dim, layers, mode):
     """The row-partitioned driver (lgc_graph_build_rect + lgc_spmm_ex + compact BPR rows) with one
     rank must reproduce the fused single-GPU step; multi-rank orchestration is covered on CPU
     (tests/test_sharded_cpu.py) and on 2+ GPUs by bench.py."""
     from gnn_ecommerce_b200 import FusedBPRTrainer
-    from gnn_ecommerce_b200.sharded import ShardedBPRTrainer
+    from gnn_ecommerce_b200.sharded import make_sharded_trainer
     g = synth.make_graph(3000, 500, 40_000, seed=13)
     ei, ew = port.df_to_graph(g.user, g.item, g.weight)
     eig, ewg = ei.to(DEV), ew.to(DEV)
@@ -343,7 +344,7 @@ def test_sharded_trainer_single_rank_equals_fused(dim, layers):
     init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, dim))
     mf = _model(g.num_nodes, dim, layers, init.numpy())
     fused = FusedBPRTrainer(mf, lr=LR)
-    sharded = ShardedBPRTrainer(eig, ewg, g.num_nodes, dim, layers, init, lr=LR)
+    sharded = make_sharded_trainer(eig, ewg, g.num_nodes, dim, layers, init, mode=mode, lr=LR)
     pl = synth.purchase_lists(g)
     rng = np.random.default_rng(2)
     for _ in range(3):

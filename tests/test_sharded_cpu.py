@@ -45,15 +45,18 @@ def _reference():
     return np.array(losses), model.embedding.weight.detach().clone(), emb
 
 
-def _worker(rank, world, port_no, out):
+def _worker(rank, world, port_no, out, mode="rows"):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _cpu_backend import CpuCheckBackend
-    from gnn_ecommerce_b200.sharded import ShardedBPRTrainer
+    from gnn_ecommerce_b200.sharded import make_sharded_trainer
     if world > 1:
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
     g, ei, ew, init, triples = _inputs()
-    tr = ShardedBPRTrainer(ei, ew, g.num_nodes, DIM, LAYERS, init, lr=LR, backend=CpuCheckBackend(), ld=DIM)
-    assert sum(tr.part.hi(r) - tr.part.lo(r) for r in range(world)) == g.num_nodes
+    tr = make_sharded_trainer(ei, ew, g.num_nodes, DIM, LAYERS, init, mode=mode, lr=LR, backend=CpuCheckBackend(),
+                              ld=DIM)
+    assert type(tr).__name__ == ("BipartiteShardedTrainer" if mode == "bipartite" else "ShardedBPRTrainer")
+    assert sum(tr.part.hi(r) - tr.part.lo(r) for r in range(world)) == (g.n_users if mode == "bipartite"
+                                                                        else g.num_nodes)
     losses = [tr.step(*t, DECAY).numpy() for t in triples]
     w, emb = tr.weight(), tr.embedding()
     if rank == 0:
@@ -64,14 +67,15 @@ def _worker(rank, world, port_no, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
-def test_sharded_step_matches_reference(world, tmp_path):
+@pytest.mark.parametrize("world,mode", [(1, "rows"), (2, "rows"), (3, "rows"), (1, "bipartite"), (2, "bipartite"),
+                                        (3, "bipartite")])
+def test_sharded_step_matches_reference(world, mode, tmp_path):
     out = str(tmp_path / "res.pt")
-    port_no = 29500 + (os.getpid() % 2000) + world
+    port_no = 29500 + (os.getpid() % 2000) + world + (10 if mode == "bipartite" else 0)
     if world == 1:
-        _worker(0, 1, port_no, out)
+        _worker(0, 1, port_no, out, mode)
     else:
-        mp.spawn(_worker, args=(world, port_no, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port_no, out, mode), nprocs=world, join=True)
     got = torch.load(out, weights_only=False)
     want_losses, want_w, want_emb = _reference()
     assert np.allclose(got["losses"], want_losses, rtol=1e-5, atol=0)
@@ -80,7 +84,15 @@ def test_sharded_step_matches_reference(world, tmp_path):
     assert float((got["w"] - want_w).abs().median()) < 1e-7
     assert rel(got["emb"], want_emb) < 5e-4
     b = got["bounds"]
-    assert b[0] == 0 and b[-1] == want_w.shape[0] and np.all(np.diff(b) >= 0)
+    assert b[0] == 0 and np.all(np.diff(b) >= 0)
+    assert b[-1] == (want_w.shape[0] if mode == "rows" else 600)
+
+
+def test_bipartite_split_detection():
+    from gnn_ecommerce_b200.sharded import bipartite_split
+    _, ei, _, _, _ = _inputs()
+    assert bipartite_split(ei) == 600
+    assert bipartite_split(torch.tensor([[0, 1, 2], [1, 2, 0]])) is None          # a triangle
 
 
 def test_row_partition_balances_cost_and_renumbers():
