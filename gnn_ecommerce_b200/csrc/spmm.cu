@@ -76,8 +76,30 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& a, size_t off, float4 
   }
 }
 
+__device__ __forceinline__ float4 final_mean(const float4* q, const EpiArgs& a, float4 s) {
+  float4 r = make_float4(__fmul_rn(q[0].x, a.ah[0]), __fmul_rn(q[0].y, a.ah[0]), __fmul_rn(q[0].z, a.ah[0]),
+                         __fmul_rn(q[0].w, a.ah[0]));
+#pragma unroll
+  for (int i = 1; i < kMaxHist; ++i)
+    if (i < a.n_hist) {
+      r.x = __fadd_rn(r.x, __fmul_rn(q[i].x, a.ah[i])); r.y = __fadd_rn(r.y, __fmul_rn(q[i].y, a.ah[i]));
+      r.z = __fadd_rn(r.z, __fmul_rn(q[i].z, a.ah[i])); r.w = __fadd_rn(r.w, __fmul_rn(q[i].w, a.ah[i]));
+    }
+  r.x = __fadd_rn(r.x, __fmul_rn(s.x, a.a1)); r.y = __fadd_rn(r.y, __fmul_rn(s.y, a.a1));
+  r.z = __fadd_rn(r.z, __fmul_rn(s.z, a.a1)); r.w = __fadd_rn(r.w, __fmul_rn(s.w, a.a1));
+  return r;
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s) {
+  if (MODE == EPI_FWD_FINAL) {
+    float4 q[kMaxHist];
+#pragma unroll
+    for (int i = 0; i < kMaxHist; ++i)
+      if (i < a.n_hist) q[i] = ldg_f4(a.hist[i] + off);
+    st_f4_cs(a.acc + off, final_mean(q, a, s));
+    return;
+  }
   Pre q;
   epi_preload<MODE>(a, off, q);
   epi_finish<MODE>(a, off, s, q);
@@ -105,14 +127,16 @@ struct LightCfg {
   static constexpr int RPS0 = (MODE == EPI_ADAM ? 256 : 512) / LD / NSUBW;
   static constexpr int RPS = RPS0 >= 8 ? 8 : (RPS0 >= 4 ? 4 : 2);      // rows per sub-warp and tile
   static constexpr int TR = RPS * NSUBW;                                // rows per tile (multiple of 4)
-  static constexpr int NBUF = MODE == EPI_ADAM ? 4 : (MODE == EPI_PLAIN ? 1 : 2);
+  static constexpr int NBUF = MODE == EPI_ADAM ? 4 : (MODE == EPI_PLAIN ? 1 : 2);   // FWD_FINAL: n_hist (run time)
   static constexpr int TILE_FLOATS = TR * LD;
   static constexpr int RP_INTS = TR + 4;                                // rowptr slice, 16-byte granular
   static constexpr int CSR_INTS = kLightStageCap + 4;                   // aligned superset of the slice
   // per stage: operand tiles | rowptr slice | src slice | w slice
-  static constexpr size_t STAGE_BYTES = (size_t)NBUF * TILE_FLOATS * 4 + RP_INTS * 4 + 2 * CSR_INTS * 4;
-  static constexpr size_t WARP_BYTES = 2 * STAGE_BYTES + 64;            // + 6 mbarriers
-  static constexpr size_t SMEM = kLightWarps * WARP_BYTES + 128;
+  static constexpr size_t stage_bytes(int nbuf) {
+    return (size_t)nbuf * TILE_FLOATS * 4 + RP_INTS * 4 + 2 * CSR_INTS * 4;
+  }
+  static constexpr size_t warp_bytes(int nbuf) { return 2 * stage_bytes(nbuf) + 64; }   // + 6 mbarriers
+  static constexpr size_t smem(int nbuf) { return kLightWarps * warp_bytes(nbuf) + 128; }
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -155,24 +179,26 @@ __global__ void __launch_bounds__(32 * kLightWarps)
 k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ w,
              const float* __restrict__ x, int num_rows, int light_max, EpiArgs args) {
   using C = LightCfg<L, V, MODE>;
-  constexpr int LD = C::LD, NSUBW = C::NSUBW, RPS = C::RPS, TR = C::TR, NBUF = C::NBUF, TF = C::TILE_FLOATS;
+  constexpr int LD = C::LD, NSUBW = C::NSUBW, RPS = C::RPS, TR = C::TR, TF = C::TILE_FLOATS;
+  const int NBUF = MODE == EPI_FWD_FINAL ? args.n_hist : C::NBUF;
+  const size_t stage_bytes = C::stage_bytes(NBUF);
   extern __shared__ __align__(128) uint8_t smem_light[];
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_light) + 127) & ~(uintptr_t)127) +
-                   (size_t)wic * C::WARP_BYTES;
-  auto stage_tiles = [&](int st) { return reinterpret_cast<float*>(wbase + (size_t)st * C::STAGE_BYTES); };
+                   (size_t)wic * C::warp_bytes(NBUF);
+  auto stage_tiles = [&](int st) { return reinterpret_cast<float*>(wbase + (size_t)st * stage_bytes); };
   auto stage_rp = [&](int st) { return reinterpret_cast<int*>(stage_tiles(st) + NBUF * TF); };
   auto stage_src = [&](int st) { return stage_rp(st) + C::RP_INTS; };
   auto stage_w = [&](int st) { return reinterpret_cast<float*>(stage_src(st) + C::CSR_INTS); };
   // barriers: [0..1] operand tiles, [2..3] rowptr slice, [4..5] CSR slice (index + stage)
-  const uint32_t bar0 = smem_addr(wbase + 2 * C::STAGE_BYTES);
+  const uint32_t bar0 = smem_addr(wbase + 2 * stage_bytes);
   const uint64_t pol = policy_evict_first();
 
   const int n_tiles = (num_rows + TR - 1) / TR;
   const int gw = blockIdx.x * kLightWarps + wic, nw = gridDim.x * kLightWarps;
   const float* in0 = MODE == EPI_PLAIN ? args.addend : (MODE == EPI_FWD_INIT ? args.xrow
-                    : (MODE == EPI_FWD_RMW ? args.acc : args.addend));
-  const uint32_t n_in = (in0 ? 1u : 0u) + (MODE == EPI_ADAM ? 3u : 0u);
+                    : (MODE == EPI_FWD_RMW ? args.acc : (MODE == EPI_FWD_FINAL ? args.hist[0] : args.addend)));
+  const uint32_t n_in = MODE == EPI_FWD_FINAL ? (uint32_t)args.n_hist : (in0 ? 1u : 0u) + (MODE == EPI_ADAM ? 3u : 0u);
 
   // lane 0: operand tiles + rowptr slice of `tile` -> ring stage `st` (two tiles ahead)
   auto request_tile = [&](int tile, int st) {
@@ -193,6 +219,9 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
       bulk_load(b + TF, args.p + goff, bytes, bar, pol);
       bulk_load(b + 2 * TF, args.m + goff, bytes, bar, pol);
       bulk_load(b + 3 * TF, args.v + goff, bytes, bar, pol);
+    }
+    if (MODE == EPI_FWD_FINAL) {
+      for (int i = 1; i < args.n_hist; ++i) bulk_load(b + i * TF, args.hist[i] + goff, bytes, bar, pol);
     }
   };
   // lane 0: once the rowptr slice of `tile` (use count `k` of stage `st`) has landed, request the
@@ -329,6 +358,12 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
           o.x = __fadd_rn(o.x, __fmul_rn(s.x, args.a1)); o.y = __fadd_rn(o.y, __fmul_rn(s.y, args.a1));
           o.z = __fadd_rn(o.z, __fmul_rn(s.z, args.a1)); o.w = __fadd_rn(o.w, __fmul_rn(s.w, args.a1));
           st_f4(buf0 + off, o);
+        } else if (MODE == EPI_FWD_FINAL) {
+          float4 q[kMaxHist];
+#pragma unroll
+          for (int i = 0; i < kMaxHist; ++i)
+            if (i < args.n_hist) q[i] = ld_f4(buf0 + i * TF + off);
+          st_f4(buf0 + off, final_mean(q, args, s));
         } else {  // EPI_ADAM
           const float4 z = ld_f4(buf0 + off);
           float4 p = ld_f4(buf1 + off), m = ld_f4(buf2 + off), vv = ld_f4(buf3 + off);
@@ -485,26 +520,32 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   const int64_t n = g->num_nodes;
   using LC = LightCfg<LL, LV, MODE>;
   {
-    static int grid_light = 0;           // per instantiation: persistent grid = SMs x resident CTAs
-    if (!grid_light) {
+    const int nbuf = MODE == EPI_FWD_FINAL ? a.n_hist : LC::NBUF;
+    const size_t smem = LC::smem(nbuf);
+    static int grid_light[kMaxHist + 1] = {};   // per instantiation and buffer count: SMs x resident CTAs
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
       LGC_CUDA(cudaFuncSetAttribute(k_spmm_light<LL, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)LC::SMEM));
+                                    (int)smem));
+      smem_set = smem;
+    }
+    if (!grid_light[nbuf]) {
       int occ = 0;
       LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_light<LL, LV, MODE>, 32 * kLightWarps,
-                                                             LC::SMEM));
-      grid_light = kNumSMs * (occ > 0 ? occ : 1);
+                                                             smem));
+      grid_light[nbuf] = kNumSMs * (occ > 0 ? occ : 1);
     }
     const int n_tiles = (int)ceil_div(n, LC::TR);
-    const int grid = (int)std::min<int64_t>(grid_light, ceil_div(n_tiles, kLightWarps));
-    ProfScope ps(PROF_LIGHT + MODE, st);
-    k_spmm_light<LL, LV, MODE><<<grid, 32 * kLightWarps, LC::SMEM, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
-                                                                        g->light_max_degree, a);
+    const int grid = (int)std::min<int64_t>(grid_light[nbuf], ceil_div(n_tiles, kLightWarps));
+    ProfScope ps(PROF_LIGHT + (MODE & 3), st);
+    k_spmm_light<LL, LV, MODE><<<grid, 32 * kLightWarps, smem, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
+                                                                    g->light_max_degree, a);
   }
   LGC_LAUNCH_CHECK();
   if (g->num_chunks > 0) {
     const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, wpb), kNumSMs * ((V == 1) ? 3 : 2));
     {
-      ProfScope ps(PROF_HEAVY + MODE, st);
+      ProfScope ps(PROF_HEAVY + (MODE & 3), st);
       k_spmm_heavy<L, V, MODE><<<grid_heavy, threads, 0, st>>>(g->chunks, (int)g->num_chunks, g->src,
                                                                 g->w_hat, x, partials, a);
     }
@@ -513,7 +554,7 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   if (g->num_split_rows > 0) {
     const int grid_fin = (int)g->num_split_rows;
     {
-      ProfScope ps(PROF_FINISH + MODE, st);
+      ProfScope ps(PROF_FINISH + (MODE & 3), st);
       k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, st>>>(g->split_rows, (int)g->num_split_rows,
                                                                partials, a);
     }
@@ -530,6 +571,7 @@ int launch_mode(const lgc_graph* g, const float* x, EpiMode mode, const EpiArgs&
     case EPI_FWD_INIT: return launch_lv<L, V, LL, LV, EPI_FWD_INIT>(g, x, a, partials, st);
     case EPI_FWD_RMW: return launch_lv<L, V, LL, LV, EPI_FWD_RMW>(g, x, a, partials, st);
     case EPI_ADAM: return launch_lv<L, V, LL, LV, EPI_ADAM>(g, x, a, partials, st);
+    case EPI_FWD_FINAL: return launch_lv<L, V, LL, LV, EPI_FWD_FINAL>(g, x, a, partials, st);
   }
   return LGC_ERR_INVALID;
 }
@@ -623,10 +665,34 @@ extern "C" int lgc_spmm_ex(const lgc_graph_t* g, int ld, const float* x, const l
   return launch_spmm(g, ld, x, (EpiMode)e->mode, a, (float*)workspace, (cudaStream_t)stream);
 }
 
+// Forward chain shared by lgc_propagate and lgc_train_step: layers 1..K-1 store x_l = A x_{l-1}
+// (plain epilogue), layer K folds the whole mean sum_l alpha_l x_l into its epilogue (FWD_FINAL).
+// `xs` holds K-1 tables. Row streams: (K-1) + (K+1) instead of the running sum's 3K-1.
+namespace lgc {
+int propagate_chain(const lgc_graph* g, int ld, int K, const float* alpha, const float* x0, float* out,
+                    float* const* xs, float* partials, cudaStream_t st) {
+  const float* cur = x0;
+  for (int l = 1; l < K; ++l) {
+    EpiArgs a;
+    a.y = xs[l - 1];
+    int rc = launch_spmm(g, ld, cur, EPI_PLAIN, a, partials, st);
+    if (rc) return rc;
+    cur = xs[l - 1];
+  }
+  EpiArgs a;
+  a.acc = out;
+  a.a1 = alpha[K];
+  a.n_hist = K;
+  a.hist[0] = x0; a.ah[0] = alpha[0];
+  for (int l = 1; l < K; ++l) { a.hist[l] = xs[l - 1]; a.ah[l] = alpha[l]; }
+  return launch_spmm(g, ld, cur, EPI_FWD_FINAL, a, partials, st);
+}
+}  // namespace lgc
+
 extern "C" size_t lgc_propagate_workspace_bytes(const lgc_graph_t* g, int ld, int num_layers) {
   if (!g) return 0;
   size_t t = (size_t)g->num_nodes * ld;
-  size_t n_tmp = num_layers > 2 ? 2 : (num_layers > 1 ? 1 : 0);
+  size_t n_tmp = num_layers > 1 ? (size_t)num_layers - 1 : 0;
   return (n_tmp * t + spmm_partials_floats(g, ld)) * sizeof(float);
 }
 
@@ -634,7 +700,7 @@ extern "C" int lgc_propagate(const lgc_graph_t* g, int ld, int num_layers, const
                              const float* x0, float* out, void* workspace, size_t workspace_bytes,
                              void* stream) {
   LGC_REQUIRE(g && h_alpha && x0 && out, "null argument");
-  LGC_REQUIRE(num_layers >= 0, "num_layers < 0");
+  LGC_REQUIRE(num_layers >= 0 && num_layers <= kMaxHist, "num_layers must be in 0..6");
   LGC_REQUIRE(x0 != out, "x0 and out must not alias");
   if (workspace_bytes < lgc_propagate_workspace_bytes(g, ld, num_layers)) {
     set_error("lgc_propagate: workspace too small");
@@ -648,24 +714,8 @@ extern "C" int lgc_propagate(const lgc_graph_t* g, int ld, int num_layers, const
     return LGC_OK;
   }
   float* ws = (float*)workspace;
-  float* tmp[2] = {ws, ws + t};
-  float* partials = ws + (num_layers > 2 ? 2 : (num_layers > 1 ? 1 : 0)) * t;
-  const float* cur = x0;
-  for (int l = 1; l <= num_layers; ++l) {
-    EpiArgs a;
-    a.acc = out;
-    a.a1 = h_alpha[l];
-    a.y = (l < num_layers) ? tmp[(l - 1) & 1] : nullptr;   // the last layer's x is never read
-    int rc;
-    if (l == 1) {
-      a.a0 = h_alpha[0];
-      a.xrow = x0;
-      rc = launch_spmm(g, ld, cur, EPI_FWD_INIT, a, partials, st);
-    } else {
-      rc = launch_spmm(g, ld, cur, EPI_FWD_RMW, a, partials, st);
-    }
-    if (rc) return rc;
-    cur = a.y;
-  }
-  return LGC_OK;
+  float* xs[kMaxHist] = {};
+  for (int l = 0; l + 1 < num_layers; ++l) xs[l] = ws + (size_t)l * t;
+  float* partials = ws + (size_t)(num_layers - 1) * t;
+  return propagate_chain(g, ld, num_layers, h_alpha, x0, out, xs, partials, st);
 }

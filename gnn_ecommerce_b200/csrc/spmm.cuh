@@ -10,8 +10,12 @@ enum EpiMode : int {
   EPI_PLAIN = 0,     // y = scale * (A x)[r] + beta * addend[r]          (LGConv; backward Horner)
   EPI_FWD_INIT = 1,  // acc = a0 * x[r] + a1 * (A x)[r];  y = (A x)[r] if y != null
   EPI_FWD_RMW = 2,   // acc += a1 * (A x)[r];             y = (A x)[r] if y != null
-  EPI_ADAM = 3       // g = scale * (A x)[r] + addend[r]; Adam update of p, m, v at row r
+  EPI_ADAM = 3,      // g = scale * (A x)[r] + addend[r]; Adam update of p, m, v at row r
+  EPI_FWD_FINAL = 4  // acc = (((hist0*ah0 + hist1*ah1) + ...) + (A x)[r]*a1): the whole layer mean of
+                     // get_embedding in ONE pass over the stored layer tables, same rounding
+                     // sequence as the reference's running sum (src/lightgcn.py:93,97)
 };
+constexpr int kMaxHist = 6;   // E0 + up to 5 stored layers (num_layers <= 6)
 
 struct AdamScalars {
   float one_minus_beta1, beta2, one_minus_beta2, bc2_sqrt, eps, neg_step_size;
@@ -27,6 +31,9 @@ struct EpiArgs {
   float* m = nullptr;
   float* v = nullptr;
   AdamScalars adam = {};
+  const float* hist[kMaxHist] = {};   // EPI_FWD_FINAL: x_0 (= E0), x_1, ..., x_{K-1}
+  float ah[kMaxHist] = {};            //                their layer weights alpha_0 .. alpha_{K-1}
+  int n_hist = 0;
 };
 
 // torch.optim.Adam (single-tensor path, no amsgrad / weight decay) on one element, with the
@@ -59,5 +66,9 @@ size_t spmm_partials_floats(const lgc_graph* g, int ld);
 // y/acc/... = epilogue(A_hat x). `partials` must hold spmm_partials_floats() floats.
 int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const EpiArgs& args,
                 float* partials, cudaStream_t stream);
+
+// out = sum_l alpha_l A^l x0 with K-1 scratch tables `xs` (see spmm.cu)
+int propagate_chain(const lgc_graph* g, int ld, int K, const float* alpha, const float* x0, float* out,
+                    float* const* xs, float* partials, cudaStream_t st);
 
 }  // namespace lgc

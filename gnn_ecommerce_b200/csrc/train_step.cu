@@ -19,7 +19,9 @@ namespace {
 
 struct StepLayout {
   size_t t;              // floats per table
-  float *xa, *xb, *out, *g, *z, *partials, *per_triple;
+  int n_x;               // scratch tables: the forward's stored layers, reused by the backward
+  float* xs[kMaxHist];
+  float *out, *g, *z, *partials, *per_triple;
   int32_t* touched;
   int* bad;
   size_t bytes;
@@ -27,7 +29,7 @@ struct StepLayout {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-StepLayout layout(const lgc_graph* g, int ld, int64_t batch, void* base) {
+StepLayout layout(const lgc_graph* g, int ld, int num_layers, int64_t batch, void* base) {
   StepLayout L;
   L.t = (size_t)g->num_nodes * ld;
   char* p = (char*)base;
@@ -35,8 +37,8 @@ StepLayout layout(const lgc_graph* g, int ld, int64_t batch, void* base) {
   auto take = [&](size_t bytes) { char* q = p ? p + off : nullptr; off += align_up(bytes, 256); return q; };
   L.g = (float*)take(L.t * 4);          // G and Z first: lgc_train_workspace_init zeroes them
   L.z = (float*)take(L.t * 4);
-  L.xa = (float*)take(L.t * 4);
-  L.xb = (float*)take(L.t * 4);
+  L.n_x = num_layers > 1 ? num_layers - 1 : 0;
+  for (int i = 0; i < kMaxHist; ++i) L.xs[i] = i < L.n_x ? (float*)take(L.t * 4) : nullptr;
   L.out = (float*)take(L.t * 4);
   L.partials = (float*)take(spmm_partials_floats(g, ld) * 4);
   L.per_triple = (float*)take((size_t)batch * 2 * 4);
@@ -74,8 +76,7 @@ using namespace lgc;
 
 extern "C" size_t lgc_train_step_workspace_bytes(const lgc_graph_t* g, int ld, int num_layers,
                                                  int64_t batch) {
-  (void)num_layers;
-  return g ? layout(g, ld, batch, nullptr).bytes : 0;
+  return g ? layout(g, ld, num_layers, batch, nullptr).bytes : 0;
 }
 
 extern "C" int lgc_train_workspace_init(const lgc_graph_t* g, int ld, int num_layers, int64_t batch,
@@ -85,8 +86,8 @@ extern "C" int lgc_train_workspace_init(const lgc_graph_t* g, int ld, int num_la
     set_error("lgc_train_workspace_init: workspace too small");
     return LGC_ERR_WORKSPACE;
   }
-  StepLayout L = layout(g, ld, batch, workspace);
-  LGC_CUDA(cudaMemsetAsync(L.g, 0, (size_t)((char*)L.xa - (char*)L.g), (cudaStream_t)stream));
+  StepLayout L = layout(g, ld, num_layers, batch, workspace);
+  LGC_CUDA(cudaMemsetAsync(L.g, 0, 2 * ((L.t * 4 + 255) / 256 * 256), (cudaStream_t)stream));
   return LGC_OK;
 }
 
@@ -94,7 +95,8 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
   LGC_REQUIRE(g && a, "null argument");
   LGC_REQUIRE(a->h_alpha && a->users && a->pos && a->neg && a->e0 && a->m && a->v && a->loss3 &&
                   a->workspace, "null field in lgc_train_step_args");
-  LGC_REQUIRE(a->num_layers >= 0 && a->batch > 0 && a->step >= 1, "bad num_layers/batch/step");
+  LGC_REQUIRE(a->num_layers >= 0 && a->num_layers <= kMaxHist && a->batch > 0 && a->step >= 1,
+              "bad num_layers/batch/step");
   LGC_REQUIRE(g->is_symmetric, "the fused step needs a symmetric normalised adjacency");
   LGC_REQUIRE(lgc_ld_supported(a->ld) && a->ld <= 256, "unsupported ld");
   if (a->workspace_bytes < lgc_train_step_workspace_bytes(g, a->ld, a->num_layers, a->batch)) {
@@ -104,8 +106,8 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
   cudaStream_t st = (cudaStream_t)stream;
   const int ld = a->ld, K = a->num_layers;
   const float* alpha = a->h_alpha;
-  StepLayout L = layout(g, ld, a->batch, a->workspace);
-  float* tmp[2] = {L.xa, L.xb};
+  StepLayout L = layout(g, ld, K, a->batch, a->workspace);
+  float* tmp[2] = {L.xs[0], L.xs[1]};       // backward ping-pong (K >= 3 has >= 2 scratch tables)
   int rc;
 
   // ---- forward: out = sum_l alpha_l A^l E0 (src/lightgcn.py:91-99)
@@ -113,22 +115,8 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
     k_scale4<<<kNumSMs * 8, 256, 0, st>>>((const float4*)a->e0, (float4*)L.out, alpha[0], (int64_t)(L.t / 4));
     LGC_LAUNCH_CHECK();
   } else {
-    const float* cur = a->e0;
-    for (int l = 1; l <= K; ++l) {
-      EpiArgs e;
-      e.acc = L.out;
-      e.a1 = alpha[l];
-      e.y = (l < K) ? tmp[(l - 1) & 1] : nullptr;
-      if (l == 1) {
-        e.a0 = alpha[0];
-        e.xrow = a->e0;
-        rc = launch_spmm(g, ld, cur, EPI_FWD_INIT, e, L.partials, st);
-      } else {
-        rc = launch_spmm(g, ld, cur, EPI_FWD_RMW, e, L.partials, st);
-      }
-      if (rc) return rc;
-      cur = e.y;
-    }
+    rc = propagate_chain(g, ld, K, alpha, a->e0, L.out, L.xs, L.partials, st);
+    if (rc) return rc;
   }
 
   // ---- loss + sparse gradients (src/lightgcn.py:123-125,279-286; src/utils_v2.py:193-211)
