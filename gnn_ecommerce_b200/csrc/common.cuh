@@ -122,7 +122,12 @@ struct lgc_graph {
   float* deg = nullptr;
   float* dis = nullptr;
   // heavy-row schedule
-  int4* chunks = nullptr;       // {row, beg, end, partial_slot or -1}
+  // (source, weight) arrays the heavy-row kernel gathers through: equal to src / w_hat except that
+  // the entries of split (hub) rows are sorted by source, so that a hub's chunks are contiguous
+  // source ranges and the chunk list can be ordered by source for L2 reuse
+  int32_t* hsrc = nullptr;
+  float* hw = nullptr;
+  int4* chunks = nullptr;       // {row, beg, end, partial_slot or -1}, ordered by first source
   int4* split_rows = nullptr;   // {row, first_slot, n_slots, 0}
   int64_t num_partial_slots = 0;   // one [ld] partial row per chunk of a split row (workspace)
 };

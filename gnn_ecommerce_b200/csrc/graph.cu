@@ -148,6 +148,34 @@ __global__ void k_fill_chunks(const int32_t* __restrict__ rowptr, int64_t num_no
   if (nc > 1) split_rows[split_off[row]] = make_int4((int)row, slot_off[row], nc, 0);
 }
 
+// segment offsets of the split (hub) rows for the segmented sort by source
+__global__ void k_split_segments(const int4* __restrict__ split_rows, int n_split, const int32_t* __restrict__ rowptr,
+                                 int32_t* __restrict__ seg_beg, int32_t* __restrict__ seg_end) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_split) return;
+  const int row = split_rows[i].x;
+  seg_beg[i] = rowptr[row];
+  seg_end[i] = rowptr[row + 1];
+}
+
+// Scheduling key of a chunk: single-chunk rows first (their sources span the whole table anyway),
+// then the chunks of the hub rows by their first source: chunks that run at the same time (the
+// heavy kernel hands chunk c to warp c mod #warps) then read the same window of the source table,
+// which is what lets L2 serve the ~3 reads of every user row.
+__global__ void k_chunk_keys(const int4* __restrict__ chunks, int n_chunks, const int32_t* __restrict__ hsrc,
+                             uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chunks) return;
+  const int4 c = chunks[i];
+  keys[i] = c.w < 0 ? 0u : (uint32_t)hsrc[c.y] + 1u;
+  vals[i] = i;
+}
+__global__ void k_chunk_gather(const int4* __restrict__ in, const int32_t* __restrict__ order, int n,
+                               int4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[order[i]];
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -191,6 +219,7 @@ extern "C" int lgc_graph_destroy(lgc_graph_t* g) {
   if (!g) return LGC_OK;
   cudaFree(g->rowptr); cudaFree(g->src); cudaFree(g->eid); cudaFree(g->w_hat);
   cudaFree(g->deg); cudaFree(g->dis); cudaFree(g->chunks); cudaFree(g->split_rows);
+  cudaFree(g->hsrc); cudaFree(g->hw);
   delete g;
   return LGC_OK;
 }
@@ -311,8 +340,49 @@ static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, co
   k_fill_chunks<<<grid_rows, threads, 0, stream>>>(rowptr.p, num_nodes, chunk_off.p, slot_off.p,
                                                    split_off.p, chunks.p, split_rows.p);
   LGC_LAUNCH_CHECK();
-  // count heavy rows on the host side from the scan tail is not available; derive on device
-  // cheaply: heavy rows = rows with n_chunks > 0 == number of distinct rows in `chunks`.
+  // ---- heavy-row gather arrays: hub rows sorted by source; chunk list ordered by first source
+  DevBuf<int32_t> hsrc, seg_beg, seg_end, ckey_vals_in, ckey_vals_out;
+  DevBuf<float> hw;
+  DevBuf<uint32_t> ckeys_in, ckeys_out;
+  DevBuf<int4> chunks_sorted;
+  DevBuf<char> tmp2;
+  LGC_CUDA(hsrc.alloc(nnz + 8)); LGC_CUDA(hw.alloc(nnz + 8));
+  LGC_CUDA(cudaMemcpyAsync(hsrc.p, src.p, (size_t)(nnz + 8) * 4, cudaMemcpyDeviceToDevice, stream));
+  LGC_CUDA(cudaMemcpyAsync(hw.p, w.p, (size_t)(nnz + 8) * 4, cudaMemcpyDeviceToDevice, stream));
+  if (h_tot[2] > 0) {
+    const int ns = h_tot[2];
+    LGC_CUDA(seg_beg.alloc(ns)); LGC_CUDA(seg_end.alloc(ns));
+    k_split_segments<<<(int)ceil_div(ns, threads), threads, 0, stream>>>(split_rows.p, ns, rowptr.p, seg_beg.p,
+                                                                         seg_end.p);
+    LGC_LAUNCH_CHECK();
+    size_t bytes = 0;
+    LGC_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, bytes, src.p, hsrc.p, w.p, hw.p, (int)nnz, ns, seg_beg.p,
+                                                 seg_end.p, stream));
+    LGC_CUDA(tmp2.alloc(bytes));
+    LGC_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp2.p, bytes, src.p, hsrc.p, w.p, hw.p, (int)nnz, ns, seg_beg.p,
+                                                 seg_end.p, stream));
+  }
+  if (h_tot[0] > 0) {
+    const int nc = h_tot[0];
+    LGC_CUDA(ckeys_in.alloc(nc)); LGC_CUDA(ckeys_out.alloc(nc));
+    LGC_CUDA(ckey_vals_in.alloc(nc)); LGC_CUDA(ckey_vals_out.alloc(nc));
+    LGC_CUDA(chunks_sorted.alloc(nc));
+    k_chunk_keys<<<(int)ceil_div(nc, threads), threads, 0, stream>>>(chunks.p, nc, hsrc.p, ckeys_in.p,
+                                                                     ckey_vals_in.p);
+    LGC_LAUNCH_CHECK();
+    size_t bytes = 0;
+    LGC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, ckeys_in.p, ckeys_out.p, ckey_vals_in.p,
+                                             ckey_vals_out.p, nc, 0, 32, stream));
+    DevBuf<char> tmp3;
+    LGC_CUDA(tmp3.alloc(bytes));
+    LGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp3.p, bytes, ckeys_in.p, ckeys_out.p, ckey_vals_in.p,
+                                             ckey_vals_out.p, nc, 0, 32, stream));
+    k_chunk_gather<<<(int)ceil_div(nc, threads), threads, 0, stream>>>(chunks.p, ckey_vals_out.p, nc,
+                                                                       chunks_sorted.p);
+    LGC_LAUNCH_CHECK();
+    LGC_CUDA(cudaStreamSynchronize(stream));      // tmp3 goes out of scope
+    std::swap(chunks.p, chunks_sorted.p);
+  }
   LGC_CUDA(cudaStreamSynchronize(stream));
 
   lgc_graph* g = new lgc_graph();
@@ -326,6 +396,7 @@ static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, co
   g->rowptr = rowptr.release(); g->src = src.release(); g->eid = eid.release();
   g->w_hat = w.release(); g->deg = deg.release(); g->dis = dis.release();
   g->chunks = chunks.release(); g->split_rows = split_rows.release();
+  g->hsrc = hsrc.release(); g->hw = hw.release();
   *out = g;
   return LGC_OK;
 }

@@ -404,57 +404,108 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
 }
 
 // ---------------------------------------------------------------------------------- heavy rows
+// Item rows: every chunk (<= 256 edges of one row) is one warp's work item. The gathers are random
+// 256-byte reads of a table far larger than L2, i.e. pure latency: the version that gathered into
+// registers (8 loads, wait, 8 FMAs, ...) sat at 21 long-scoreboard stalls per issued instruction.
+// Here the neighbour rows are copied with cp.async (LDGSTS: no destination register, no in-order
+// wait) into a per-warp shared-memory ring of kHeavyStages groups of R rows, kHeavyStages-1 groups
+// ahead of the FMAs, so ~12 KB per warp are in flight all the time.
+constexpr int kHeavyWarps = 4;         // warps per CTA (independent: no CTA barrier)
+constexpr int kHeavyStages = 4;
+
+template <int L, int V>
+struct HeavyCfg {
+  static constexpr int LD = 4 * L * V;
+  static constexpr int RPW = 32 / L;                                   // edge streams per warp
+  static constexpr int R0 = 4096 / (LD * 4);                           // ~4 KB of rows per group
+  static constexpr int R = R0 < 2 * RPW ? 2 * RPW : (R0 / RPW * RPW);  // rows per group (multiple of RPW)
+  static constexpr int EPL = R / RPW;                                  // edges per lane-stream and group
+  static constexpr size_t GROUP_BYTES = (size_t)R * LD * 4 + (size_t)R * 4;   // rows + their weights
+  static constexpr size_t WARP_BYTES = kHeavyStages * ((GROUP_BYTES + 15) / 16 * 16);
+  static constexpr size_t SMEM = kHeavyWarps * WARP_BYTES + 16;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc) : "memory");
+}
+
 template <int L, int V, int MODE>
-__global__ void __launch_bounds__(256, (V == 1) ? 3 : 2)
+__global__ void __launch_bounds__(32 * kHeavyWarps)
 k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks, const int32_t* __restrict__ src,
              const float* __restrict__ w, const float* __restrict__ x, float* __restrict__ partials,
              EpiArgs args) {
-  constexpr int RPW = 32 / L;        // edge streams per warp
-  constexpr int LD = 4 * L * V;
-  constexpr int U = (L >= 8) ? 8 : L;  // gathers in flight per stream and unrolled step
-  const int lane = threadIdx.x & 31;
+  using C = HeavyCfg<L, V>;
+  constexpr int LD = C::LD, RPW = C::RPW, R = C::R, EPL = C::EPL, S = kHeavyStages;
+  extern __shared__ __align__(16) uint8_t smem_heavy[];
+  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wbase = smem_heavy + (size_t)wic * C::WARP_BYTES;
+  auto slot_rows = [&](int sl_) { return reinterpret_cast<float*>(wbase + (size_t)sl_ * (C::WARP_BYTES / S)); };
+  auto slot_w = [&](int sl_) { return slot_rows(sl_) + R * LD; };
   const int sub = lane / L, sl = lane % L;
-  // persistent: the grid is sized to the resident warps; chunk c goes to warp c mod #warps, so
-  // every warp gets the same mix of long (hub) and short chunks and no CTA slot idles on a tail
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int c_idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c_idx < num_chunks; c_idx += n_warps) {
+  // persistent: chunk c goes to warp c mod #warps (every warp gets the same mix of hub and short chunks)
+  const int n_warps = gridDim.x * kHeavyWarps;
+  for (int c_idx = blockIdx.x * kHeavyWarps + wic; c_idx < num_chunks; c_idx += n_warps) {
     const int4 c = chunks[c_idx];
     const int row = c.x, beg = c.y, end = c.z, slot = c.w;
+    const int n_groups = (end - beg + R - 1) / R;
+
+    // stream `sub` of group g takes edges beg + g*R + i*RPW + sub, i < EPL
+    int idx[EPL]; float wgt[EPL];
+    auto load_idx = [&](int g) {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int e = beg + g * R + i * RPW + sub;
+        idx[i] = -1; wgt[i] = 0.f;
+        if (g < n_groups && e < end) { idx[i] = src[e]; wgt[i] = w[e]; }
+      }
+    };
+    auto issue = [&](int g) {                       // uses idx/wgt loaded for group g
+      if (g < n_groups) {
+        float* rows = slot_rows(g % S);
+        float* ws = slot_w(g % S);
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+          const int r = i * RPW + sub;
+          if (idx[i] >= 0) {
+            const float* xr = x + (size_t)idx[i] * LD + 4 * sl;
+#pragma unroll
+            for (int v = 0; v < V; ++v) cp_async16(rows + r * LD + 4 * (sl + L * v), xr + 4 * L * v);
+          }
+          if (sl == 0) ws[r] = wgt[i];             // 0 for the padding of the last group
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // one group per step, empty or not
+    };
 
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // (source, weight) of the next 32 edges are requested before the current 32 are gathered
-    int nxt_s = 0; float nxt_w = 0.f;
-    if (beg + lane < end) { nxt_s = src[beg + lane]; nxt_w = w[beg + lane]; }
-    for (int base = beg; base < end; base += 32) {
-      const int my_s = nxt_s; const float my_w = nxt_w;
-      if (base + 32 + lane < end) { nxt_s = src[base + 32 + lane]; nxt_w = w[base + 32 + lane]; }
-      const int n = min(32, end - base);
-      // stream `sub` takes entries sub, sub+RPW, ... of this block of 32
+    __syncwarp();                                   // the previous chunk's last reads of the ring are done
+#pragma unroll 1
+    for (int g = 0; g < S - 1; ++g) { load_idx(g); issue(g); }
+    load_idx(S - 1);
+#pragma unroll 1
+    for (int g = 0; g < n_groups; ++g) {
+      issue(g + S - 1);                             // into the slot consumed in the previous iteration
+      load_idx(g + S);                              // indices one group ahead of their issue
+      asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+      __syncwarp();                                 // every lane's copies of group g have landed
+      const float* rows = slot_rows(g % S);
+      const float* ws = slot_w(g % S);
+      const int n_here = min(R, end - beg - g * R);
 #pragma unroll
-      for (int t0 = 0; t0 < L; t0 += U) {
-        float ww[U]; float4 xv[U][V];
+      for (int i = 0; i < EPL; ++i) {
+        const int r = i * RPW + sub;
+        if (r < n_here) {
+          const float wv = ws[r];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int idx = (t0 + u) * RPW + sub;
-          const int s = __shfl_sync(0xffffffffu, my_s, idx);
-          ww[u] = __shfl_sync(0xffffffffu, my_w, idx);
-          if (idx < n) {
-            const float* xr = x + (size_t)s * LD + 4 * sl;
-#pragma unroll
-            for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
-          }
+          for (int v = 0; v < V; ++v) acc[v] = fma4(wv, ld_f4(rows + r * LD + 4 * (sl + L * v)), acc[v]);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if ((t0 + u) * RPW + sub < n) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] = fma4(ww[u], xv[u][v], acc[v]);
-          }
       }
+      __syncwarp();                                 // slot g % S may be refilled
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // combine the RPW edge streams (fixed order: deterministic)
 #pragma unroll
     for (int o = L; o < 32; o <<= 1) {
@@ -516,7 +567,7 @@ __global__ void __launch_bounds__(256) k_spmm_finish(const int4* __restrict__ sp
 // (few lanes per row: more rows per warp instruction, more gathers in flight per lane)
 template <int L, int V, int LL, int LV, int MODE>
 int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
-  const int threads = 256, wpb = threads / 32;
+  const int threads = 256;
   const int64_t n = g->num_nodes;
   using LC = LightCfg<LL, LV, MODE>;
   {
@@ -543,11 +594,21 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   }
   LGC_LAUNCH_CHECK();
   if (g->num_chunks > 0) {
-    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, wpb), kNumSMs * ((V == 1) ? 3 : 2));
+    using HC = HeavyCfg<L, V>;
+    static int grid_heavy_max = 0;       // per instantiation: persistent grid = SMs x resident CTAs
+    if (!grid_heavy_max) {
+      LGC_CUDA(cudaFuncSetAttribute(k_spmm_heavy<L, V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)HC::SMEM));
+      int occ = 0;
+      LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_heavy<L, V, MODE>, 32 * kHeavyWarps,
+                                                             HC::SMEM));
+      grid_heavy_max = kNumSMs * (occ > 0 ? occ : 1);
+    }
+    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, kHeavyWarps), grid_heavy_max);
     {
       ProfScope ps(PROF_HEAVY + (MODE & 3), st);
-      k_spmm_heavy<L, V, MODE><<<grid_heavy, threads, 0, st>>>(g->chunks, (int)g->num_chunks, g->src,
-                                                                g->w_hat, x, partials, a);
+      k_spmm_heavy<L, V, MODE><<<grid_heavy, 32 * kHeavyWarps, HC::SMEM, st>>>(
+          g->chunks, (int)g->num_chunks, g->hsrc, g->hw, x, partials, a);
     }
     LGC_LAUNCH_CHECK();
   }
@@ -601,7 +662,7 @@ int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const 
   if (rs.L == HL && rs.V == HV) return launch_mode<HL, HV, LL, LV>(g, x, mode, a, partials, st);
   // light-row geometry == heavy-row geometry: narrower sub-warps (4 lanes x 4 float4) measured
   // 1.5x slower -- 8 rows per warp instruction hit the same shared-memory banks in the epilogue
-  LGC_CASE(16, 1, 16, 1) LGC_CASE(16, 2, 16, 2) LGC_CASE(16, 3, 16, 3) LGC_CASE(16, 4, 16, 4)
+  LGC_CASE(16, 1, 8, 2) LGC_CASE(16, 2, 16, 2) LGC_CASE(16, 3, 16, 3) LGC_CASE(16, 4, 16, 4)
   LGC_CASE(8, 1, 8, 1) LGC_CASE(8, 3, 8, 3) LGC_CASE(8, 5, 8, 5)
   LGC_CASE(4, 1, 4, 1) LGC_CASE(4, 3, 4, 3) LGC_CASE(4, 5, 4, 5)
   LGC_CASE(2, 1, 2, 1) LGC_CASE(1, 1, 1, 1)
