@@ -208,6 +208,22 @@ int lgc_train_workspace_init(const lgc_graph_t* graph, int ld, int num_layers, i
                              void* workspace, size_t workspace_bytes, void* stream);
 int lgc_train_step(const lgc_graph_t* graph, const lgc_train_step_args* args, void* stream);
 
+/* ------------------------------------------------------------------ batch_loader (src/utils_v2.py:168-181)
+ * Device-side BPR sampler: `batch` triples (user, pos, neg), all outputs int64 on the device.
+ *   users  distinct purchasers, uniform without replacement        (random.sample, :174)
+ *   pos    uniform over the user's train purchases                 (random.choice, :178)
+ *   neg    uniform item id + n_users outside the user's ignore list (rejection, :169-173,179)
+ * Inputs are the CSR form of `train_pos_list_df` (src/utils_v2.py:64-89): purchasers [P];
+ * pos_ptr [P+1] / pos_items (offset item ids); ign_ptr [P+1] / ign_items (offset item ids,
+ * SORTED within a user). Draws are a pure function of (seed, step, triple index): the same call
+ * reproduces the same batch. batch > P fails like random.sample ("Sample larger than population"). */
+size_t lgc_sample_triples_workspace_bytes(int64_t n_purchasers, int64_t batch);
+int lgc_sample_triples(int64_t n_purchasers, const int64_t* purchasers, const int64_t* pos_ptr,
+                       const int64_t* pos_items, const int64_t* ign_ptr, const int64_t* ign_items,
+                       int64_t n_users, int64_t n_items, int64_t batch, uint64_t seed, uint64_t step,
+                       int64_t* users, int64_t* pos, int64_t* neg, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ------------------------------------------------------------------ recommendK (src/lightgcn.py:169-182)
  * Top-k items for a list of users from the final embeddings:
  *   pred = user_emb[user_ids] @ item_emb^T                      (src/lightgcn.py:173)
