@@ -311,9 +311,7 @@ def main():
         sc = bench_scoring(embedding(), g, dev, args, pk, dim, world, rank)
         if rank == 0:
             emit({"scoring": sc})
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return finish(world, trainer)
     dev_triples = [tuple(torch.from_numpy(x).to(dev) for x in t) for t in triples]
     pin_triples = [tuple(torch.from_numpy(x).pin_memory() for x in t) for t in triples]
 
@@ -361,12 +359,18 @@ def main():
     # ---- per-kernel-class durations (CUDA events on the launching stream) over K more steps
     n_tags = 24
     ms_arr, cnt_arr = (C.c_double * n_tags)(), (C.c_longlong * n_tags)()
+    if world > 1:
+        trainer.use_graph = False          # per-kernel events need eager launches
+    eager0 = lib.lgc_launch_count()
     lib.lgc_profile_enable(1)
     for i in range(args.steps):
         step(*dev_triples[args.warmup + i])
     torch.cuda.synchronize()
     lib.lgc_profile_read(ms_arr, cnt_arr, n_tags)
     lib.lgc_profile_enable(0)
+    if world > 1:
+        trainer.use_graph = True
+        launches = lib.lgc_launch_count() - eager0   # graph replays re-run these launches step for step
     light_ms = sum(ms_arr[t] for t in range(0, 4))
     light_cnt = sum(cnt_arr[t] for t in range(0, 4))
     heavy_ms = sum(ms_arr[t] for t in range(4, 8))
@@ -383,9 +387,7 @@ def main():
             score = {"error": repr(e)}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return finish(world, trainer)
 
     alg = algorithmic_bytes(g, ld, layers, nnz)
     light_avg_ms = light_ms / max(light_cnt, 1)
@@ -453,8 +455,21 @@ def main():
         "scoring": score,
     }
     emit(line)
+    return finish(world, trainer)
+
+
+def finish(world, trainer):
+    """Multi-rank teardown: drop the captured CUDA graph (it holds NCCL work) before the process
+    group goes away, then leave without running interpreter-exit destructors in an arbitrary order."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        import torch.distributed as dist
+        if hasattr(trainer, "release_graph"):
+            trainer.release_graph()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -35,7 +35,7 @@ class SpmmEpilogue(C.Structure):
     _fields_ = [("mode", c_i32), ("a0", c_f32), ("a1", c_f32), ("scale", c_f32), ("beta", c_f32),
                 ("y", c_vp), ("acc", c_vp), ("xrow", c_vp), ("addend", c_vp), ("p", c_vp), ("m", c_vp),
                 ("v", c_vp), ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("eps", c_f64),
-                ("step", c_i64)]
+                ("step", c_i64), ("adam_scalars", c_vp)]
 
 
 class ScoreTopkArgs(C.Structure):
@@ -69,6 +69,8 @@ _SIGNATURES = {
                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgc_scatter_add_rows": (C.c_int, [c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "lgc_adam_step": (C.c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_f64, c_f64, c_f64, c_f64, c_i64, c_vp]),
+    "lgc_adam_scalars": (C.c_int, [c_f64, c_f64, c_f64, c_f64, c_i64, C.POINTER(c_f32)]),
+    "lgc_adam_step_dev": (C.c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgc_train_step_workspace_bytes": (c_sz, [c_vp, C.c_int, C.c_int, c_i64]),
     "lgc_train_workspace_init": (C.c_int, [c_vp, C.c_int, C.c_int, c_i64, c_vp, c_sz, c_vp]),
     "lgc_train_step": (C.c_int, [c_vp, C.POINTER(TrainStepArgs), c_vp]),

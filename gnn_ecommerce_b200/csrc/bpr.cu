@@ -163,7 +163,9 @@ __global__ void k_scatter_add_rows(int n, int ld, const int64_t* __restrict__ id
 }
 
 __global__ void k_adam(int64_t n4, float4* __restrict__ p, const float4* __restrict__ g,
-                       float4* __restrict__ m, float4* __restrict__ v, AdamScalars s) {
+                       float4* __restrict__ m, float4* __restrict__ v, AdamScalars s_host,
+                       const AdamScalars* __restrict__ s_dev) {
+  const AdamScalars s = s_dev ? *s_dev : s_host;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = __ldcs(g + i), mm = __ldcs(m + i), vv = __ldcs(v + i);
@@ -176,7 +178,9 @@ __global__ void k_adam(int64_t n4, float4* __restrict__ p, const float4* __restr
 }
 
 __global__ void k_adam_tail(int64_t beg, int64_t n, float* __restrict__ p, const float* __restrict__ g,
-                            float* __restrict__ m, float* __restrict__ v, AdamScalars s) {
+                            float* __restrict__ m, float* __restrict__ v, AdamScalars s_host,
+                            const AdamScalars* __restrict__ s_dev) {
+  const AdamScalars s = s_dev ? *s_dev : s_host;
   int64_t i = beg + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) adam_update(p[i], m[i], v[i], g[i], s);
 }
@@ -250,23 +254,42 @@ extern "C" int lgc_bpr_loss_grad(int64_t num_nodes, int ld, int64_t batch, const
   return rc;
 }
 
-extern "C" int lgc_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr,
-                             double beta1, double beta2, double eps, int64_t step, void* stream) {
+static int adam_launch(int64_t n, float* p, const float* g, float* m, float* v, AdamScalars s,
+                       const AdamScalars* s_dev, cudaStream_t st) {
   LGC_REQUIRE(p && g && m && v, "null argument");
-  LGC_REQUIRE(n >= 0 && step >= 1, "bad size or step");
+  LGC_REQUIRE(n >= 0, "bad size");
   LGC_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0,
               "buffers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  AdamScalars s = make_adam_scalars(lr, beta1, beta2, eps, step);
   const int64_t n4 = n / 4;
   if (n4) {
     int grid = (int)std::min<int64_t>(ceil_div(n4, 256), kNumSMs * 16);
-    k_adam<<<grid, 256, 0, st>>>(n4, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, s);
+    k_adam<<<grid, 256, 0, st>>>(n4, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, s, s_dev);
     LGC_LAUNCH_CHECK();
   }
   if (n % 4) {
-    k_adam_tail<<<1, 32, 0, st>>>(n4 * 4, n, p, g, m, v, s);
+    k_adam_tail<<<1, 32, 0, st>>>(n4 * 4, n, p, g, m, v, s, s_dev);
     LGC_LAUNCH_CHECK();
   }
   return LGC_OK;
+}
+
+extern "C" int lgc_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr,
+                             double beta1, double beta2, double eps, int64_t step, void* stream) {
+  LGC_REQUIRE(step >= 1, "bad step");
+  return adam_launch(n, p, g, m, v, make_adam_scalars(lr, beta1, beta2, eps, step), nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int lgc_adam_scalars(double lr, double beta1, double beta2, double eps, int64_t step, float* h_out6) {
+  LGC_REQUIRE(h_out6 && step >= 1, "bad argument");
+  const AdamScalars s = make_adam_scalars(lr, beta1, beta2, eps, step);
+  h_out6[0] = s.one_minus_beta1; h_out6[1] = s.beta2; h_out6[2] = s.one_minus_beta2;
+  h_out6[3] = s.bc2_sqrt; h_out6[4] = s.eps; h_out6[5] = s.neg_step_size;
+  return LGC_OK;
+}
+
+extern "C" int lgc_adam_step_dev(int64_t n, float* p, const float* g, float* m, float* v,
+                                 const float* d_scalars6, void* stream) {
+  LGC_REQUIRE(d_scalars6, "null scalars");
+  return adam_launch(n, p, g, m, v, AdamScalars{}, reinterpret_cast<const AdamScalars*>(d_scalars6),
+                     (cudaStream_t)stream);
 }

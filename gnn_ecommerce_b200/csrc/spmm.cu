@@ -66,10 +66,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& a, size_t off, float4 
     st_f4_cs(a.acc + off, o);
   } else {  // EPI_ADAM
     float4 p = q.r1, m = q.r2, v = q.r3;
-    adam_update(p.x, m.x, v.x, fmaf(a.scale, s.x, q.r0.x), a.adam);
-    adam_update(p.y, m.y, v.y, fmaf(a.scale, s.y, q.r0.y), a.adam);
-    adam_update(p.z, m.z, v.z, fmaf(a.scale, s.z, q.r0.z), a.adam);
-    adam_update(p.w, m.w, v.w, fmaf(a.scale, s.w, q.r0.w), a.adam);
+    const AdamScalars ad = a.adam_dev ? *a.adam_dev : a.adam;
+    adam_update(p.x, m.x, v.x, fmaf(a.scale, s.x, q.r0.x), ad);
+    adam_update(p.y, m.y, v.y, fmaf(a.scale, s.y, q.r0.y), ad);
+    adam_update(p.z, m.z, v.z, fmaf(a.scale, s.z, q.r0.z), ad);
+    adam_update(p.w, m.w, v.w, fmaf(a.scale, s.w, q.r0.w), ad);
     st_f4(a.p + off, p);
     st_f4_cs(a.m + off, m);
     st_f4_cs(a.v + off, v);
@@ -367,10 +368,11 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
         } else {  // EPI_ADAM
           const float4 z = ld_f4(buf0 + off);
           float4 p = ld_f4(buf1 + off), m = ld_f4(buf2 + off), vv = ld_f4(buf3 + off);
-          adam_update(p.x, m.x, vv.x, fmaf(args.scale, s.x, z.x), args.adam);
-          adam_update(p.y, m.y, vv.y, fmaf(args.scale, s.y, z.y), args.adam);
-          adam_update(p.z, m.z, vv.z, fmaf(args.scale, s.z, z.z), args.adam);
-          adam_update(p.w, m.w, vv.w, fmaf(args.scale, s.w, z.w), args.adam);
+          const AdamScalars ad = args.adam_dev ? *args.adam_dev : args.adam;
+          adam_update(p.x, m.x, vv.x, fmaf(args.scale, s.x, z.x), ad);
+          adam_update(p.y, m.y, vv.y, fmaf(args.scale, s.y, z.y), ad);
+          adam_update(p.z, m.z, vv.z, fmaf(args.scale, s.z, z.z), ad);
+          adam_update(p.w, m.w, vv.w, fmaf(args.scale, s.w, z.w), ad);
           st_f4(buf1 + off, p);
           st_f4(buf2 + off, m);
           st_f4(buf3 + off, vv);
@@ -718,8 +720,10 @@ extern "C" int lgc_spmm_ex(const lgc_graph_t* g, int ld, const float* x, const l
     case LGC_EPI_FWD_INIT: LGC_REQUIRE(e->acc && e->xrow, "FWD_INIT needs acc and xrow"); break;
     case LGC_EPI_FWD_RMW: LGC_REQUIRE(e->acc, "FWD_RMW needs acc"); break;
     case LGC_EPI_ADAM:
-      LGC_REQUIRE(e->addend && e->p && e->m && e->v && e->step >= 1, "ADAM needs addend, p, m, v, step >= 1");
-      a.adam = make_adam_scalars(e->lr, e->beta1, e->beta2, e->eps, e->step);
+      LGC_REQUIRE(e->addend && e->p && e->m && e->v && (e->step >= 1 || e->adam_scalars),
+                  "ADAM needs addend, p, m, v and step >= 1 (or device scalars)");
+      if (e->adam_scalars) a.adam_dev = reinterpret_cast<const AdamScalars*>(e->adam_scalars);
+      else a.adam = make_adam_scalars(e->lr, e->beta1, e->beta2, e->eps, e->step);
       break;
     default: LGC_REQUIRE(false, "unknown epilogue mode");
   }

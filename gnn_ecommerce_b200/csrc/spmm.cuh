@@ -31,6 +31,7 @@ struct EpiArgs {
   float* m = nullptr;
   float* v = nullptr;
   AdamScalars adam = {};
+  const AdamScalars* adam_dev = nullptr;   // if set: scalars live in device memory (CUDA-graph replay)
   const float* hist[kMaxHist] = {};   // EPI_FWD_FINAL: x_0 (= E0), x_1, ..., x_{K-1}
   float ah[kMaxHist] = {};            //                their layer weights alpha_0 .. alpha_{K-1}
   int n_hist = 0;

@@ -48,6 +48,7 @@ class RowPartition:
         self.world, self.num_nodes = world, n
         self.max_rows = int(max(1, np.diff(self.bounds).max()))
         self.max_rows = (self.max_rows + 3) // 4 * 4
+        self._cache = {}
 
     def lo(self, rank: int) -> int:
         return int(self.bounds[rank])
@@ -55,14 +56,20 @@ class RowPartition:
     def hi(self, rank: int) -> int:
         return int(self.bounds[rank + 1])
 
+    def _dev(self, device):
+        key = str(device)
+        if key not in self._cache:
+            self._cache[key] = (torch.as_tensor(self.bounds[1:], device=device),
+                                torch.as_tensor(self.bounds[:-1], device=device))
+        return self._cache[key]
+
     def owner(self, ids: Tensor) -> Tensor:
-        b = torch.as_tensor(self.bounds[1:], device=ids.device)
-        return torch.bucketize(ids, b, right=True)
+        return torch.bucketize(ids, self._dev(ids.device)[0], right=True)
 
     def padded_id(self, ids: Tensor) -> Tensor:
         """Global node id -> row of the all-gathered `[world * max_rows, ld]` table."""
         own = self.owner(ids)
-        lo = torch.as_tensor(self.bounds[:-1], device=ids.device)[own]
+        lo = self._dev(ids.device)[1][own]
         return own * self.max_rows + (ids - lo)
 
     def unpad(self, table: Tensor) -> Tensor:
@@ -74,6 +81,7 @@ class RowPartition:
 # --------------------------------------------------------------------------------- CUDA backend
 class CudaBackend:
     """The product backend: raw pointers into liblgc_b200.so. No CPU path."""
+    supports_graph = True
 
     def __init__(self):
         from . import _capi
@@ -107,11 +115,12 @@ class CudaBackend:
 
     def spmm_ex(self, handle, ld: int, x: Tensor, ws: Tensor, mode: int, *, y=None, acc=None, xrow=None,
                 addend=None, a0=0.0, a1=0.0, scale=1.0, beta=0.0, p=None, m=None, v=None, lr=0.0,
-                betas=(0.9, 0.999), eps=1e-8, step=1) -> None:
+                betas=(0.9, 0.999), eps=1e-8, step=1, adam_scalars=None) -> None:
         from .graph import _ptr, _stream
         e = self._capi.SpmmEpilogue(mode=mode, a0=a0, a1=a1, scale=scale, beta=beta, y=_ptr(y), acc=_ptr(acc),
                                     xrow=_ptr(xrow), addend=_ptr(addend), p=_ptr(p), m=_ptr(m), v=_ptr(v),
-                                    lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, step=step)
+                                    lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, step=step,
+                                    adam_scalars=_ptr(adam_scalars))
         with torch.cuda.device(x.device):
             rc = self._lib.lgc_spmm_ex(handle, ld, _ptr(x), C.byref(e), _ptr(ws), ws.numel(), _stream())
         self._capi.check(rc, "lgc_spmm_ex")
@@ -124,9 +133,24 @@ class CudaBackend:
                                                 _ptr(rows.contiguous()), _ptr(table), _stream())
         self._capi.check(rc, "lgc_scatter_add_rows")
 
-    def adam_step(self, p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, betas, eps: float, step: int):
+    def adam_step(self, p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, betas, eps: float, step: int,
+                  adam_scalars=None):
         from . import ops
-        ops.adam_step(p, g.contiguous(), m, v, lr, betas, eps, step)
+        if adam_scalars is None:
+            ops.adam_step(p, g.contiguous(), m, v, lr, betas, eps, step)
+            return
+        from .graph import _ptr, _stream
+        g = g.contiguous()
+        with torch.cuda.device(p.device):
+            rc = self._lib.lgc_adam_step_dev(p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(adam_scalars),
+                                             _stream())
+        self._capi.check(rc, "lgc_adam_step_dev")
+
+    def adam_scalars(self, lr: float, betas, eps: float, step: int) -> Tensor:
+        """The 6 step-dependent Adam scalars as a fresh host tensor (float32[6])."""
+        arr = (C.c_float * 6)()
+        self._capi.check(self._lib.lgc_adam_scalars(lr, betas[0], betas[1], eps, step, arr), "lgc_adam_scalars")
+        return torch.tensor(list(arr), dtype=torch.float32)
 
     def bpr(self, outc: Tensor, e0c: Tensor, batch: int, decay: float, alpha0: float):
         """BPR + L2 on the compact `[3*batch, ld]` row tables (users | pos | neg)."""
@@ -138,8 +162,60 @@ class CudaBackend:
         return loss3, gc, zc
 
 
+# --------------------------------------------------------------------------------- CUDA-graph replay
+class _GraphedStep:
+    """`step()` for both sharded trainers. A sharded step is ~100 small launches (kernels through
+    the C ABI, NCCL collectives, index plumbing) issued from Python: beyond 4 GPUs the host cannot
+    issue them as fast as the GPUs retire them. So after two eager steps the whole step -- NCCL
+    included -- is captured into one CUDA graph and replayed; the only per-step host work is copying
+    the triples into static buffers and refreshing the six Adam scalars (launch arguments are frozen
+    in a graph, so the update kernels read them from device memory)."""
+    use_graph = True
+
+    def _adam_kw(self):
+        return {"adam_scalars": self._adam_dev} if self._adam_dev is not None else {}
+
+    def _init_graph_state(self):
+        self._graph, self._graph_key, self._warm = None, None, 0
+        self._graphable = bool(getattr(self.backend, "supports_graph", False)) and self.dev.type == "cuda"
+        self._adam_dev = None
+        if self._graphable:
+            self._adam_dev = torch.zeros(6, dtype=torch.float32, device=self.dev)
+
+    def step(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
+        self.step_count += 1
+        users, pos, neg = (t.to(device=self.dev, dtype=torch.int64) for t in (users, pos, neg))
+        if not self._graphable:
+            return self._step_impl(users, pos, neg, decay)
+        # a fresh pageable host tensor per step: the copy is staged before this call returns, so the
+        # host running ahead of the GPU cannot overwrite scalars a queued step has not read yet
+        self._adam_dev.copy_(self.backend.adam_scalars(self.lr, self.betas, self.eps, self.step_count))
+        key = (users.numel(), float(decay))
+        if not self.use_graph or (self._graph_key != key and self._warm < 2):
+            self._warm += 1
+            return self._step_impl(users, pos, neg, decay)
+        if self._graph_key != key:
+            self._static = [users.clone(), pos.clone(), neg.clone()]
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._static_loss = self._step_impl(*self._static, decay)
+            self._graph, self._graph_key = graph, key
+        else:
+            for dst, src in zip(self._static, (users, pos, neg)):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss.clone()
+
+    def release_graph(self) -> None:
+        """Drop the captured graph (call before destroying the process group)."""
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        self._graph, self._graph_key, self._static_loss = None, None, None
+
+
 # --------------------------------------------------------------------------------- trainer
-class ShardedBPRTrainer:
+class ShardedBPRTrainer(_GraphedStep):
     """`step()` = one mini-batch of `mini_batch_loop` over `world` GPUs; same results as the
     single-GPU fused step up to fp32 summation order (row sums are identical: every row is still
     reduced by one rank in CSR order)."""
@@ -184,6 +260,7 @@ class ShardedBPRTrainer:
         self.out, self.y, self.z = table(self.max_rows), table(self.max_rows), table(self.max_rows)
         self.full = [table(self.n_cols), table(self.n_cols)]
         self.gfull = table(self.n_cols)                       # dL/d out, padded-global layout, sparse
+        self._init_graph_state()
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -226,10 +303,9 @@ class ShardedBPRTrainer:
         return self.part.unpad(full)[:, : self.dim]
 
     # ------------------------------------------------------------------ one mini-batch
-    def step(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
+    def _step_impl(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
         b, a, K, ld = self.backend, self.alpha, self.layers, self.ld
         batch = users.numel()
-        self.step_count += 1
         self.propagate()
 
         # ---- the <= 3*batch needed rows of out / E0: owners contribute, one small all-reduce
@@ -256,7 +332,7 @@ class ShardedBPRTrainer:
             self._all_gather(cur, self.y)
             scale = 1.0
         b.spmm_ex(self.handle, ld, cur, self.ws, 3, addend=self.z, scale=scale, p=self.e0, m=self.m, v=self.v,
-                  lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count)
+                  lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, **self._adam_kw())
         self.gfull.index_fill_(0, pid, 0.0)
         self.z.index_fill_(0, locc, 0.0)
         return loss3
@@ -287,7 +363,7 @@ def bipartite_split(edge_index: Tensor) -> Optional[int]:
     return s if bool((lo_side[0] != lo_side[1]).all()) and s > 0 else None
 
 
-class BipartiteShardedTrainer:
+class BipartiteShardedTrainer(_GraphedStep):
     """Bipartite-aware sharding of the same step (~30x less traffic than the
     all-gather of whole tables): USERS are partitioned over the ranks (balanced by in-degree + 4),
     the small ITEM table is replicated. Per layer a rank computes its users' rows from the replicated
@@ -347,6 +423,7 @@ class BipartiteShardedTrainer:
         self.part_i = table(ni)                                              # partial item sums
         self.g_u, self.z_u, self.g_i, self.z_i = table(nu), table(nu), table(ni), table(ni)
         self.n_cols = self.n_items                                           # rows exchanged per layer
+        self._init_graph_state()
 
     def __del__(self):
         for name in ("gu", "gi"):
@@ -385,10 +462,9 @@ class BipartiteShardedTrainer:
         return self.out_u, self.out_i
 
     # ------------------------------------------------------------------ one mini-batch
-    def step(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
+    def _step_impl(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
         b, a, K, ld, s = self.backend, self.alpha, self.layers, self.ld, self.n_users
         batch = users.numel()
-        self.step_count += 1
         self.propagate()
 
         users = users.to(device=self.dev, dtype=torch.int64)
@@ -418,11 +494,12 @@ class BipartiteShardedTrainer:
             cu, ci, scale = nu, ni, 1.0
         yi = self._item_rows(cu, self.part_i)
         b.spmm_ex(self.gu, ld, ci, self.ws_u, 3, addend=self.z_u, scale=scale, p=self.e0_u, m=self.m_u, v=self.v_u,
-                  lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count)
+                  lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, **self._adam_kw())
         if scale != 1.0:
             yi.mul_(scale)
         yi.add_(self.z_i)
-        b.adam_step(self.e0_i, yi, self.m_i, self.v_i, self.lr, self.betas, self.eps, self.step_count)
+        b.adam_step(self.e0_i, yi, self.m_i, self.v_i, self.lr, self.betas, self.eps, self.step_count,
+                    **self._adam_kw())
         self.g_u.index_fill_(0, locc, 0.0)
         self.z_u.index_fill_(0, locc, 0.0)
         self.g_i.index_fill_(0, items, 0.0)

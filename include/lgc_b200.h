@@ -130,6 +130,8 @@ typedef struct {
   float* v;
   double lr, beta1, beta2, eps;
   int64_t step;
+  const float* adam_scalars;   /* optional DEVICE pointer to the 6 floats of lgc_adam_scalars(): lets a
+                                  captured CUDA graph replay the launch with a new step count */
 } lgc_spmm_epilogue;
 int lgc_spmm_ex(const lgc_graph_t* graph, int ld, const float* x, const lgc_spmm_epilogue* epilogue,
                 void* workspace, size_t workspace_bytes, void* stream);
@@ -176,6 +178,12 @@ int lgc_scatter_add_rows(int64_t n, int ld, const int64_t* idx, const float* row
  * parameters are doubles (Python floats in the reference) and rounded to fp32 where torch does. */
 int lgc_adam_step(int64_t n, float* p, const float* g, float* m, float* v, double lr, double beta1,
                   double beta2, double eps, int64_t step, void* stream);
+/* The step-dependent scalars of that update as 6 HOST floats {1-beta1, beta2, 1-beta2,
+ * sqrt(1-beta2^t), eps, -lr/(1-beta1^t)}, and the same update reading them from DEVICE memory
+ * (launch arguments of a captured CUDA graph are frozen; the scalars are refreshed by a copy). */
+int lgc_adam_scalars(double lr, double beta1, double beta2, double eps, int64_t step, float* h_out6);
+int lgc_adam_step_dev(int64_t n, float* p, const float* g, float* m, float* v, const float* d_scalars6,
+                      void* stream);
 
 /* ------------------------------------------------------------------ fused training step
  * One iteration of `mini_batch_loop` (src/train_lightgcn.py:129-151) for pre-sampled triples:

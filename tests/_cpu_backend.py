@@ -27,7 +27,7 @@ class CpuCheckBackend:
         return torch.empty(1)
 
     def spmm_ex(self, h, ld, x, ws, mode, *, y=None, acc=None, xrow=None, addend=None, a0=0.0, a1=0.0, scale=1.0,
-                beta=0.0, p=None, m=None, v=None, lr=0.0, betas=(0.9, 0.999), eps=1e-8, step=1):
+                beta=0.0, p=None, m=None, v=None, lr=0.0, betas=(0.9, 0.999), eps=1e-8, step=1, adam_scalars=None):
         n = h["n_rows"]
         assert x.shape == (h["n_cols"], ld)
         s = torch.zeros(n, ld).index_add_(0, h["dst"], h["w"][:, None] * x[h["src"]])
@@ -58,7 +58,7 @@ class CpuCheckBackend:
         keep = idx >= 0
         table.index_add_(0, idx[keep], rows[keep])        # CPU index_add_ is sequential: deterministic
 
-    def adam_step(self, p, g, m, v, lr, betas, eps, step):
+    def adam_step(self, p, g, m, v, lr, betas, eps, step, adam_scalars=None):
         f = torch.float32
         b1, b2 = betas
         bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step

@@ -347,14 +347,15 @@ def test_sharded_trainer_single_rank_equals_fused(dim, layers, mode):
     sharded = make_sharded_trainer(eig, ewg, g.num_nodes, dim, layers, init, mode=mode, lr=LR)
     pl = synth.purchase_lists(g)
     rng = np.random.default_rng(2)
-    for _ in range(3):
+    for _ in range(5):                 # steps 1-2 eager, step 3 captures a CUDA graph, 4-5 replay it
         u, p, n = (torch.from_numpy(x).to(DEV) for x in synth.sample_triples(pl, 200, g.n_users, g.n_items, rng))
         a = fused.step(eig, ewg, u, p, n, DECAY).cpu().numpy()
         b = sharded.step(u, p, n, DECAY).cpu().numpy()
         assert np.allclose(a, b, rtol=2e-5)
+    assert sharded._graph is not None
     wf, ws = mf.embedding.weight.detach().cpu(), sharded.weight().cpu()
     assert ws.shape == (g.num_nodes, dim)
-    assert rel(ws, wf) < 5e-4 and np.median(np.abs(ws.numpy() - wf.numpy())) < 1e-7
+    assert rel(ws, wf) < 1e-3 and np.median(np.abs(ws.numpy() - wf.numpy())) < 1e-7
     with torch.no_grad():
         ef = mf.get_embedding(eig, ewg).cpu()
     assert rel(sharded.embedding().cpu(), ef) < 5e-4
