@@ -439,11 +439,14 @@ class BipartiteShardedTrainer(_GraphedStep):
         if self.world > 1:
             dist.all_reduce(t, group=self.group)
 
-    def _item_rows(self, x_u: Tensor, out: Tensor) -> Tensor:
-        """out = (A_hat x)[items] = all-reduce of every rank's partial sums over its own users."""
+    def _item_rows(self, x_u: Tensor, out: Tensor):
+        """out = (A_hat x)[items] = all-reduce of every rank's partial sums over its own users.
+        The all-reduce is ASYNCHRONOUS: the caller launches the (independent) user-row SpMM of the
+        same layer next and waits on the returned handle only when it needs the item rows, so the
+        NVLink exchange hides behind the HBM-bound kernel."""
         self.backend.spmm_ex(self.gi, self.ld, x_u, self.ws_i, 0, y=out, scale=1.0)
-        self._all_reduce(out)
-        return out
+        work = dist.all_reduce(out, group=self.group, async_op=True) if self.world > 1 else None
+        return out, work
 
     # ------------------------------------------------------------------ forward only
     def propagate(self) -> Tuple[Tensor, Tensor]:
@@ -452,9 +455,11 @@ class BipartiteShardedTrainer(_GraphedStep):
         for l in range(1, K + 1):
             last = l == K
             nu, ni = self.xu[l & 1], self.xi[l & 1]
-            yi = self._item_rows(cu, self.part_i if last else ni)
+            yi, work = self._item_rows(cu, self.part_i if last else ni)
             b.spmm_ex(self.gu, self.ld, ci, self.ws_u, 1 if l == 1 else 2, y=None if last else nu, acc=self.out_u,
                       xrow=self.e0_u, a0=a[0], a1=a[l])
+            if work is not None:
+                work.wait()
             if l == 1:
                 torch.mul(self.e0_i, a[0], out=self.out_i)
             self.out_i.add_(yi, alpha=a[l])                    # replicated epilogue of the item rows
@@ -486,15 +491,19 @@ class BipartiteShardedTrainer(_GraphedStep):
         cu, ci, scale = self.g_u, self.g_i, a[K]
         for l in range(K - 1, 0, -1):                         # h_l = alpha_l G + A h_{l+1}
             nu, ni = self.xu[l & 1], self.xi[l & 1]
-            yi = self._item_rows(cu, ni)
+            yi, work = self._item_rows(cu, ni)
             b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=nu, addend=self.g_u, scale=scale, beta=a[l])
+            if work is not None:
+                work.wait()
             if scale != 1.0:
                 yi.mul_(scale)
             yi.add_(self.g_i, alpha=a[l])
             cu, ci, scale = nu, ni, 1.0
-        yi = self._item_rows(cu, self.part_i)
+        yi, work = self._item_rows(cu, self.part_i)
         b.spmm_ex(self.gu, ld, ci, self.ws_u, 3, addend=self.z_u, scale=scale, p=self.e0_u, m=self.m_u, v=self.v_u,
                   lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, **self._adam_kw())
+        if work is not None:
+            work.wait()
         if scale != 1.0:
             yi.mul_(scale)
         yi.add_(self.z_i)
