@@ -680,7 +680,8 @@ struct RescoreMeta {          // lanes 0..15 own one user of the step each
 
 template <bool PIPE>
 __global__ void __launch_bounds__(256, 2)
-k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int list_cap, int64_t user0, int n_items,
+k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int n_tiles, int list_cap, int64_t user0,
+          int n_items,
           int d, const float* __restrict__ user_emb, int ld_user, const int64_t* __restrict__ user_ids,
           const float* __restrict__ item_emb, int ld_item, const float* __restrict__ thr_exact,
           const int64_t* __restrict__ seen_ptr, const int64_t* __restrict__ seen_items,
@@ -692,21 +693,29 @@ k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int lis
   float4* s_items = reinterpret_cast<float4*>(smem_rs);                 // [128][row_f4]
   float4* s_rows = s_items + 128 * row_f4;                              // [8 warps][16][d4]
 
-  const int tile = blockIdx.x, item0 = tile * kTileN;
-  if (min(grp_off[tile * 8], list_cap) >= min(grp_off[tile * 8 + 8], list_cap)) return;
-  for (int i = threadIdx.x; i < 128 * d4; i += 256) {
-    const int r = i / d4, c = i % d4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (item0 + r < n_items) v = load_row_f4(item_emb + (size_t)(item0 + r) * ld_item, c, d);
-    s_items[r * row_f4 + c] = v;
+  // Load balance: candidate lists are heavily skewed towards the tiles of popular items (a trained
+  // model sends most users to the same few hundred items), so CTAs do not own tiles: CTA c owns
+  // the slice [c * Q, (c + 1) * Q) of the GLOBAL list (sorted by group, hence by tile) and walks
+  // the tiles its slice touches, re-staging the 128 item rows when the tile changes.
+  const int n_groups = n_tiles * 8;
+  const long long total = min((long long)grp_off[n_groups], (long long)list_cap);
+  long long q = (total + gridDim.x - 1) / gridDim.x;
+  q = (q + kRowsPerWarp - 1) / kRowsPerWarp * kRowsPerWarp;
+  const long long lo_ll = (long long)blockIdx.x * q, hi_ll = min(total, lo_ll + q);
+  if (lo_ll >= hi_ll) return;
+  const int lo = (int)lo_ll, hi = (int)hi_ll;
+  // first group whose slice reaches beyond `lo`
+  int g_lo = 0;
+  {
+    int a = 0, b = n_groups;
+    while (a < b) { const int m = (a + b) >> 1; if (grp_off[m + 1] <= lo) a = m + 1; else b = m; }
+    g_lo = a;
   }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int it = lane & 15, hw = lane >> 4;
   float4* rows = s_rows + (size_t)warp * kRowsPerWarp * d4;
   unsigned long long my_emit = 0;
-  const int step = gridDim.y * 8 * kRowsPerWarp;
-
+  const int step = 8 * kRowsPerWarp;
   auto load_meta = [&](int e0, int end) {
     RescoreMeta m; m.u = 0; m.uid = 0; m.sb = 0; m.thr = INFINITY; m.n_seen = 0;
     if (e0 < end && lane < min(kRowsPerWarp, end - e0)) {
@@ -737,11 +746,23 @@ k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int lis
   };
 
 #pragma unroll 1
+  for (int tile = g_lo >> 3; tile < n_tiles && min(grp_off[tile * 8], list_cap) < hi; ++tile) {
+  const int item0 = tile * kTileN;
+  __syncthreads();                                   // every warp is done with the previous tile's rows
+  for (int i = threadIdx.x; i < 128 * d4; i += 256) {
+    const int r = i / d4, c = i % d4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (item0 + r < n_items) v = load_row_f4(item_emb + (size_t)(item0 + r) * ld_item, c, d);
+    s_items[r * row_f4 + c] = v;
+  }
+  __syncthreads();
+#pragma unroll 1
   for (int g = 0; g < 8; ++g) {
-    const int beg = min(grp_off[tile * 8 + g], list_cap), end = min(grp_off[tile * 8 + g + 1], list_cap);
+    const int beg = max(lo, min(grp_off[tile * 8 + g], list_cap));
+    const int end = min(hi, min(grp_off[tile * 8 + g + 1], list_cap));
     const int local = g * kGroup + it, item = item0 + local;
     const float4* irow = s_items + local * row_f4;
-    int e0 = beg + (blockIdx.y * 8 + warp) * kRowsPerWarp;
+    int e0 = beg + warp * kRowsPerWarp;
     if (e0 >= end) continue;
     // software pipeline (PIPE: d <= 64, one float4 column per lane and row): metadata two steps
     // ahead, user rows one step ahead, so neither latency is exposed behind the dot products
@@ -817,6 +838,7 @@ k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int lis
       m0 = m1; m1 = m2;
     }
   }
+  }   // tiles of this CTA's slice
   if (my_emit) atomicAdd(&sc->n_emitted, my_emit);
 }
 
@@ -930,7 +952,7 @@ k_select(int n_users, int64_t user0, int n_items, int k, uint8_t* flag, const in
 // ------------------------------------------------------------------------------------ exhaustive path
 // Persistent CTAs over the fallback list: all masked fp32 scores of one user into a scratch row,
 // then k rounds of block-wide selection in the same total order.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restrict__ sc, int64_t user0,
              int n_items, int d, int k, const float* __restrict__ user_emb, int ld_user,
              const int64_t* __restrict__ user_ids, const float* __restrict__ item_emb, int ld_item,
@@ -939,8 +961,8 @@ k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restric
   extern __shared__ __align__(16) uint8_t smem_ex[];
   const int d4 = (d + 3) >> 2;
   float4* s_user = reinterpret_cast<float4*>(smem_ex);
-  __shared__ float s_bs[8];
-  __shared__ int s_bi[8];
+  __shared__ float s_bs[32];
+  __shared__ int s_bi[32];
   __shared__ float s_ps;
   __shared__ int s_pi;
   float* my = scratch + (size_t)blockIdx.x * n_items;
@@ -952,7 +974,7 @@ k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restric
     const int64_t uid = user_ids ? user_ids[user0 + u] : user0 + u;
     const float* urow = user_emb + (size_t)uid * ld_user;
     __syncthreads();
-    for (int c = threadIdx.x; c < d4; c += 256) {
+    for (int c = threadIdx.x; c < d4; c += blockDim.x) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       v.x = urow[4 * c];
       if (4 * c + 1 < d) v.y = urow[4 * c + 1];
@@ -961,7 +983,7 @@ k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restric
       s_user[c] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_items; i += 256) {
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
       const float* irow = item_emb + (size_t)i * ld_item;
       float s0 = 0.f, s1 = 0.f;
       for (int c = 0; c < d4; ++c) {
@@ -982,7 +1004,7 @@ k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restric
     }
     __syncthreads();
     if (seen_ptr) {
-      for (int64_t q = seen_ptr[user0 + u] + threadIdx.x; q < seen_ptr[user0 + u + 1]; q += 256) {
+      for (int64_t q = seen_ptr[user0 + u] + threadIdx.x; q < seen_ptr[user0 + u + 1]; q += blockDim.x) {
         const int64_t si = seen_items[q];
         if (si >= 0 && si < n_items) my[si] = 0.f;          // multiplicative mask
       }
@@ -992,7 +1014,7 @@ k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restric
     for (int r = 0; r < k; ++r) {
       const float ps = s_ps; const int pi = s_pi;
       float bs = -INFINITY; int bi = 0x7fffffff;
-      for (int i = threadIdx.x; i < n_items; i += 256) {
+      for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
         const float s = my[i];
         if (before(ps, pi, s, i) && before(s, i, bs, bi)) { bs = s; bi = i; }
       }
@@ -1005,7 +1027,7 @@ k_exhaustive(const int32_t* __restrict__ fb_users, const ScoreScalars* __restric
       if (lane == 0) { s_bs[warp] = bs; s_bi[warp] = bi; }
       __syncthreads();
       if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
           if (before(s_bs[w], s_bi[w], bs, bi)) { bs = s_bs[w]; bi = s_bi[w]; }
         const bool found = bi != 0x7fffffff;
         topk_items[(size_t)(user0 + u) * k + r] = found ? bi : -1;
@@ -1280,18 +1302,17 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     }
     {
       ProfScope ps(PROF_SCORE_RESCORE, st);
-      const int rsplits = (int)std::max<int64_t>(1, ceil_div(kNumSMs * 12, L.n_tiles));
-      dim3 grid(L.n_tiles, rsplits);
+      const int grid = kNumSMs * 8;        // slices of the global candidate list (4 waves of 2 CTAs/SM)
       if (d4 <= 16)
-        k_rescore<true><<<grid, 256, rs_smem, st>>>(list, tile_off, L.list_cap, user0, (int)a->n_items, a->d,
-                                                    a->user_emb, a->ld_user, a->user_ids, a->item_emb, a->ld_item,
-                                                    thr_exact, a->seen_ptr, a->seen_items, flag, cnt, citem, cscore,
-                                                    sc);
+        k_rescore<true><<<grid, 256, rs_smem, st>>>(list, tile_off, L.n_tiles, L.list_cap, user0, (int)a->n_items,
+                                                    a->d, a->user_emb, a->ld_user, a->user_ids, a->item_emb,
+                                                    a->ld_item, thr_exact, a->seen_ptr, a->seen_items, flag, cnt,
+                                                    citem, cscore, sc);
       else
-        k_rescore<false><<<grid, 256, rs_smem, st>>>(list, tile_off, L.list_cap, user0, (int)a->n_items, a->d,
-                                                     a->user_emb, a->ld_user, a->user_ids, a->item_emb, a->ld_item,
-                                                     thr_exact, a->seen_ptr, a->seen_items, flag, cnt, citem, cscore,
-                                                     sc);
+        k_rescore<false><<<grid, 256, rs_smem, st>>>(list, tile_off, L.n_tiles, L.list_cap, user0, (int)a->n_items,
+                                                     a->d, a->user_emb, a->ld_user, a->user_ids, a->item_emb,
+                                                     a->ld_item, thr_exact, a->seen_ptr, a->seen_items, flag, cnt,
+                                                     citem, cscore, sc);
       LGC_LAUNCH_CHECK();
     }
     {
@@ -1303,7 +1324,7 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     }
     {
       ProfScope ps(PROF_SCORE_EXHAUSTIVE, st);
-      k_exhaustive<<<L.n_exh_ctas, 256, ex_smem, st>>>(fb, sc, user0, (int)a->n_items, a->d, a->k, a->user_emb,
+      k_exhaustive<<<L.n_exh_ctas, 1024, ex_smem, st>>>(fb, sc, user0, (int)a->n_items, a->d, a->k, a->user_emb,
                                                        a->ld_user, a->user_ids, a->item_emb, a->ld_item, a->seen_ptr,
                                                        a->seen_items, scratch, a->topk_items, a->topk_scores);
       LGC_LAUNCH_CHECK();

@@ -80,6 +80,8 @@ class LightGCN(torch.nn.Module):
         self.convs = ModuleList([LGConv(**kwargs) for _ in range(num_layers)])
         self._normalize = bool(kwargs.get("normalize", True))
         self._alpha_host = None
+        self._emb_cache = None          # (key, table): final embeddings for serving / evaluation
+        self._weights_epoch = 0         # bumped by FusedBPRTrainer (it updates the table through raw pointers)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -98,6 +100,19 @@ class LightGCN(torch.nn.Module):
     def graph(self, edge_index: Adj, edge_weight: OptTensor) -> Graph:
         _require_cuda(edge_index, "edge_index")
         return graph_for(edge_index, edge_weight, self.num_nodes, self._normalize)
+
+    def cached_embedding(self, edge_index: Adj, edge_weight: OptTensor) -> Tensor:
+        """Final embeddings for scoring, computed once per (weights, graph) instead of on every
+        `recommendK` / TorchServe request as the reference does (`src/lightgcn.py:171`,
+        `torchserve/lightgcn_handler.py:91`). No autograd graph is kept."""
+        w = self.embedding.weight
+        key = (w.data_ptr(), w._version, self._weights_epoch, edge_index.data_ptr(), edge_index._version,
+               tuple(edge_index.shape), None if edge_weight is None else (edge_weight.data_ptr(), edge_weight._version),
+               self.alpha._version, self.num_layers)
+        if self._emb_cache is None or self._emb_cache[0] != key:
+            with torch.no_grad():
+                self._emb_cache = (key, self.get_embedding(edge_index, edge_weight).detach())
+        return self._emb_cache[1]
 
     # ------------------------------------------------------------------ reference API
     def get_embedding(self, edge_index: Adj, edge_weight: OptTensor) -> Tensor:
@@ -124,8 +139,7 @@ class LightGCN(torch.nn.Module):
                   k: int = 1, edge_weight: OptTensor = None) -> Tensor:
         """Top-k of out[src] @ out[dst]^T (reference `src/lightgcn.py:138-167`; the reference
         forgets `edge_weight` there and raises -- it is an optional extra argument here)."""
-        with torch.no_grad():
-            out = self.get_embedding(edge_index, edge_weight)
+        out = self.cached_embedding(edge_index, edge_weight)
         src = torch.arange(self.num_nodes, device=out.device) if src_index is None else src_index
         dst = out if dst_index is None else out[dst_index]
         items, _ = scoring.score_topk(out, dst.contiguous(), src, None, None, k)
@@ -141,8 +155,7 @@ class LightGCN(torch.nn.Module):
         device) or a `scoring.SeenLists` CSR; masking is multiplicative like the reference's
         (`pred * (1 - mask)`: a seen item scores 0.0). Returns the same two-column frame
         (`user_ID`, `top_rlvnt_itm`)."""
-        with torch.no_grad():
-            embeds = self.get_embedding(edge_index, edge_weight)
+        embeds = self.cached_embedding(edge_index, edge_weight)
         seen = scoring.as_seen_lists(interactions_t, len(user_id_list), n_items, embeds.device)
         users = torch.as_tensor(np.asarray(user_id_list, dtype=np.int64), device=embeds.device)
         rows = ops.full_rows(embeds)

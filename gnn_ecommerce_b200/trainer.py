@@ -101,6 +101,7 @@ class FusedBPRTrainer:
         with torch.cuda.device(rows.device):
             rc = self._lib.lgc_train_step(g.handle, C.byref(args), _stream())
         _capi.check(rc, "lgc_train_step")
+        model._weights_epoch = getattr(model, "_weights_epoch", 0) + 1     # invalidates cached_embedding
         return loss3
 
     def zero_grad(self, set_to_none: bool = True) -> None:   # API symmetry with torch.optim

@@ -194,3 +194,33 @@ def test_full_width_property_c4_slice():
     sub_ptr = np.concatenate([[0], np.cumsum(ptr[sample + 1] - ptr[sample])])
     sub_items = np.concatenate([items[ptr[u]:ptr[u + 1]] for u in sample] + [np.zeros(0, np.int64)])
     _check_topk(ue, ie, sample, sub_ptr, sub_items, 20, top[sample], sc[sample])
+
+
+def test_embedding_cache_is_reused_and_invalidated():
+    """Serving path: `recommendK` propagates once per (weights, graph); a fused
+    training step or an in-place weight change invalidates the cached table."""
+    from gnn_ecommerce_b200 import FusedBPRTrainer, LightGCN, ops
+    g = synth.make_graph(1500, 300, 15_000, seed=4)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    model = LightGCN(g.num_nodes, 32, 2).to(DEV)
+    calls = {"n": 0}
+    orig = ops.propagate
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    ops.propagate = counting
+    try:
+        users = list(range(50))
+        a = model.recommendK(eig, ewg, g.n_users, g.n_items, None, users, 10)
+        b = model.recommendK(eig, ewg, g.n_users, g.n_items, None, users, 10)
+        assert calls["n"] == 1 and a["top_rlvnt_itm"].tolist() == b["top_rlvnt_itm"].tolist()
+        pl = synth.purchase_lists(g)
+        u, p, n = (torch.from_numpy(x).to(DEV) for x in synth.sample_triples(pl, 64, g.n_users, g.n_items,
+                                                                            np.random.default_rng(0)))
+        FusedBPRTrainer(model, lr=0.05).step(eig, ewg, u, p, n, 1e-4)
+        model.recommendK(eig, ewg, g.n_users, g.n_items, None, users, 10)
+        assert calls["n"] == 2                       # the fused step itself runs inside lgc_train_step
+    finally:
+        ops.propagate = orig
