@@ -587,7 +587,8 @@ template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, int u_pad, int n_users,
        const float* __restrict__ thr_grp, int* __restrict__ grp_cnt, const int* __restrict__ grp_off,
-       int* __restrict__ grp_cur, int* __restrict__ list, int list_cap, uint8_t* __restrict__ flag) {
+       int* __restrict__ grp_cur, int* __restrict__ list, int list_cap, uint8_t* __restrict__ flag,
+       uint8_t* __restrict__ hitmask) {
   const int tile = blockIdx.x;
   const int per = round_up((n_users + gridDim.y - 1) / gridDim.y, 1024);
   const int u_beg = blockIdx.y * per, u_end = min(n_users, u_beg + per);
@@ -595,6 +596,30 @@ k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, 
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   int my[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (FILL) {
+    // second pass: the count pass left one byte per (tile, user) with the hit groups
+    for (int u0 = u_beg; u0 < u_end; u0 += 1024) {
+      unsigned hm[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = u0 + threadIdx.x + 256 * j;
+        hm[j] = u < u_end ? (unsigned)__ldcs(hitmask + (size_t)tile * u_pad + u) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = u0 + threadIdx.x + 256 * j;
+        unsigned hits = hm[j];
+        while (hits) {
+          const int g = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const int pos = grp_off[tile * 8 + g] + atomicAdd(&grp_cur[tile * 8 + g], 1);
+          if (pos < list_cap) list[pos] = u;
+          else flag[u] = 2;                            // picked up by k_select -> exhaustive path
+        }
+      }
+    }
+    return;
+  }
   for (int u0 = u_beg; u0 < u_end; u0 += 1024) {
     float thr[4]; uint32_t tw[4];
 #pragma unroll
@@ -607,28 +632,20 @@ k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, 
     for (int j = 0; j < 4; ++j) {
       const int u = u0 + threadIdx.x + 256 * j;
       const float up = __half2float(__ushort_as_half((unsigned short)(tw[j] >> 16)));
-      if (!(up >= thr[j])) continue;
       unsigned hits = 0;
-      const uint4 rec = __ldcs(reinterpret_cast<const uint4*>(gmax16) + (size_t)tile * u_pad + u);
-      const uint32_t w[4] = {rec.x, rec.y, rec.z, rec.w};
+      if (up >= thr[j]) {
+        const uint4 rec = __ldcs(reinterpret_cast<const uint4*>(gmax16) + (size_t)tile * u_pad + u);
+        const uint32_t w[4] = {rec.x, rec.y, rec.z, rec.w};
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[p]));
-        if (f.x >= thr[j]) hits |= 1u << (2 * p);
-        if (f.y >= thr[j]) hits |= 1u << (2 * p + 1);
-      }
-      if (!FILL) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) my[g] += (hits >> g) & 1;
-      } else {
-        while (hits) {
-          const int g = __ffs(hits) - 1;
-          hits &= hits - 1;
-          const int pos = grp_off[tile * 8 + g] + atomicAdd(&grp_cur[tile * 8 + g], 1);
-          if (pos < list_cap) list[pos] = u;
-          else flag[u] = 2;                            // picked up by k_select -> exhaustive path
+        for (int p = 0; p < 4; ++p) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[p]));
+          if (f.x >= thr[j]) hits |= 1u << (2 * p);
+          if (f.y >= thr[j]) hits |= 1u << (2 * p + 1);
         }
       }
+      if (u < u_end) hitmask[(size_t)tile * u_pad + u] = (uint8_t)hits;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) my[g] += (hits >> g) & 1;
     }
   }
   if (!FILL) {
@@ -1050,7 +1067,7 @@ __global__ void k_add_stats(const ScoreScalars* __restrict__ sc, int64_t* __rest
 struct Layout {
   int kp, katoms, n_stages, n_tiles, i_pad, chunk, chunk_pad, ts, list_cap;
   size_t gemm_smem;
-  size_t off_scal, off_b16, off_bnorm, off_btile, off_a16, off_anorm, off_g16, off_g128, off_tcnt, off_toff, off_tcur, off_list, off_thr_grp, off_thr_exact, off_flag,
+  size_t off_scal, off_b16, off_bnorm, off_btile, off_a16, off_anorm, off_g16, off_g128, off_tcnt, off_toff, off_tcur, off_list, off_hit, off_thr_grp, off_thr_exact, off_flag,
       off_fb, off_cnt, off_citem, off_cscore, off_scratch;
   int n_exh_ctas;
   size_t bytes;
@@ -1074,7 +1091,7 @@ bool make_layout(int64_t n_users, int64_t n_items, int d, int k, Layout* L) {
   L->n_tiles = L->i_pad / kTileN;
   // bytes per user of the chunk-sized buffers
   const size_t per_user = (size_t)L->kp * 2 + 4 + (size_t)L->n_tiles * 4 * 4 + (size_t)L->n_tiles * 4 + 4 + 4 + 1 +
-                          4 + 4 + (size_t)kCap * 8 + 40 * 4;
+                          4 + 4 + (size_t)kCap * 8 + 40 * 4 + (size_t)L->n_tiles;
   const size_t fixed = (size_t)L->i_pad * (L->kp * 2 + 8) + (size_t)296 * n_items * 4 + (1 << 16);
   int64_t chunk = round_up(n_users, kUserBlock);
   if (fixed + per_user * (size_t)chunk > kWorkspaceBudget) {
@@ -1102,6 +1119,7 @@ bool make_layout(int64_t n_users, int64_t n_items, int d, int k, Layout* L) {
   L->off_toff = take((size_t)(L->n_tiles * 8 + 1) * 4);
   L->off_tcur = take((size_t)(L->n_tiles * 8 + 1) * 4);
   L->off_list = take((size_t)L->list_cap * 4);
+  L->off_hit = take((size_t)L->n_tiles * cp);
   L->off_thr_grp = take(cp * 4);
   L->off_thr_exact = take(cp * 4);
   L->off_flag = take(cp);
@@ -1184,6 +1202,7 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
   int* tile_off = (int*)(ws + L.off_toff);
   int* tile_cur = (int*)(ws + L.off_tcur);
   int* list = (int*)(ws + L.off_list);
+  uint8_t* hitmask = ws + L.off_hit;
   float* thr_grp = (float*)(ws + L.off_thr_grp);
   float* thr_exact = (float*)(ws + L.off_thr_exact);
   uint8_t* flag = ws + L.off_flag;
@@ -1292,12 +1311,12 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
                                                                       ceil_div(nu, 1024)));
       dim3 sgrid(L.n_tiles, ssplits);
       k_scan<false><<<sgrid, 256, 0, st>>>(g128, g16, L.chunk_pad, nu, thr_grp, tile_cnt, tile_off, tile_cur, list,
-                                          L.list_cap, flag);
+                                          L.list_cap, flag, hitmask);
       LGC_LAUNCH_CHECK();
       k_group_prefix<<<1, 256, 0, st>>>(tile_cnt, L.n_tiles * 8, tile_off, sc);
       LGC_LAUNCH_CHECK();
       k_scan<true><<<sgrid, 256, 0, st>>>(g128, g16, L.chunk_pad, nu, thr_grp, tile_cnt, tile_off, tile_cur, list,
-                                         L.list_cap, flag);
+                                         L.list_cap, flag, hitmask);
       LGC_LAUNCH_CHECK();
     }
     {
