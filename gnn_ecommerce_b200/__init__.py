@@ -8,7 +8,8 @@ library has not been built.
 """
 from . import synth  # noqa: F401  (numpy only)
 
-__all__ = ["LightGCN", "LGConv", "BPRLoss", "FusedBPRTrainer", "SeenLists", "score_topk", "synth"]
+__all__ = ["LightGCN", "LGConv", "BPRLoss", "FusedBPRTrainer", "SeenLists", "score_topk", "synth",
+           "DeviceSampler", "save_model", "load_model", "make_sharded_trainer"]
 
 
 def __getattr__(name):
@@ -21,4 +22,13 @@ def __getattr__(name):
     if name in ("SeenLists", "score_topk"):
         from . import scoring
         return getattr(scoring, name)
+    if name == "DeviceSampler":
+        from .sampler import DeviceSampler
+        return DeviceSampler
+    if name in ("save_model", "load_model"):
+        from . import checkpoint
+        return getattr(checkpoint, name)
+    if name == "make_sharded_trainer":
+        from .sharded import make_sharded_trainer
+        return make_sharded_trainer
     raise AttributeError(name)

@@ -131,3 +131,58 @@ extern "C" int lgc_sample_triples(int64_t n_purchasers, const int64_t* purchaser
   LGC_LAUNCH_CHECK();
   return LGC_OK;
 }
+
+// ------------------------------------------------------------------ MARK_MAPK on the device
+// precision@k / recall@k of reference `LightGCN.MARK_MAPK` (src/lightgcn.py:184-189) for every
+// evaluated user at once: overlap = |set(held-out items) & set(top-k)|, recall = overlap /
+// len(held-out list), precision = overlap / k; then the two means. One thread per user (lists are
+// short), means reduced in double precision in a fixed order.
+namespace lgc {
+namespace {
+__global__ void k_mark_mapk(long long n_users, int k, const int64_t* __restrict__ topk,
+                            const int64_t* __restrict__ held_ptr, const int64_t* __restrict__ held_items,
+                            float* __restrict__ per_user) {
+  const long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  const long long hb = held_ptr[u], hn = held_ptr[u + 1] - hb;
+  int overlap = 0;
+  for (int j = 0; j < k; ++j) {
+    const int64_t it = topk[u * k + j];
+    bool dup = false;                                   // set semantics on the top-k side
+    for (int q = 0; q < j; ++q) dup |= (topk[u * k + q] == it);
+    if (dup) continue;
+    bool hit = false;
+    for (long long q = 0; q < hn; ++q) hit |= (held_items[hb + q] == it);
+    overlap += hit ? 1 : 0;
+  }
+  per_user[2 * u] = (float)overlap / (float)k;
+  per_user[2 * u + 1] = hn > 0 ? (float)overlap / (float)hn : 0.f;
+}
+__global__ void k_mean2(const float* __restrict__ per_user, long long n, double* __restrict__ out2) {
+  __shared__ double s_a[256], s_b[256];
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 256) { a += per_user[2 * i]; b += per_user[2 * i + 1]; }
+  s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { s_a[threadIdx.x] += s_a[threadIdx.x + o]; s_b[threadIdx.x] += s_b[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out2[0] = n ? s_a[0] / (double)n : 0.0; out2[1] = n ? s_b[0] / (double)n : 0.0; }
+}
+}  // namespace
+}  // namespace lgc
+
+extern "C" int lgc_mark_mapk(int64_t n_users, int k, const int64_t* topk_items, const int64_t* held_ptr,
+                             const int64_t* held_items, float* per_user, double* out2, void* stream) {
+  LGC_REQUIRE(topk_items && held_ptr && held_items && per_user && out2, "null argument");
+  LGC_REQUIRE(n_users >= 0 && k >= 1, "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_users > 0) {
+    k_mark_mapk<<<(int)ceil_div(n_users, 256), 256, 0, st>>>(n_users, k, topk_items, held_ptr, held_items, per_user);
+    LGC_LAUNCH_CHECK();
+  }
+  k_mean2<<<1, 256, 0, st>>>(per_user, n_users, out2);
+  LGC_LAUNCH_CHECK();
+  return LGC_OK;
+}

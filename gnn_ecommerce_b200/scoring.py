@@ -105,3 +105,24 @@ def score_topk(user_emb: Tensor, item_emb: Tensor, user_ids: Optional[Tensor],
         rc = lib.lgc_score_topk(C.byref(args), _stream())
     _capi.check(rc, "lgc_score_topk")
     return (items, scores, stats) if return_stats else (items, scores)
+
+
+def mark_mapk(topk_items: Tensor, held_ptr: Tensor, held_items: Tensor):
+    """Device-side `MARK_MAPK` (reference `src/lightgcn.py:184-189`): returns
+    `(mean precision@k, mean recall@k, per_user [U, 2])` for top-k lists already on the device
+    (row i of `topk_items` and row i of the held-out CSR belong to the same user)."""
+    lib = _capi.lib()
+    dev = topk_items.device
+    if not topk_items.is_cuda:
+        raise RuntimeError("mark_mapk needs CUDA tensors (no CPU fallback)")
+    top = topk_items.to(torch.int64).contiguous()
+    ptr = held_ptr.to(device=dev, dtype=torch.int64).contiguous()
+    items = held_items.to(device=dev, dtype=torch.int64).contiguous()
+    n, k = top.shape
+    per_user = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    out2 = torch.empty(2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.lgc_mark_mapk(n, k, _ptr(top), _ptr(ptr), _ptr(items), _ptr(per_user), _ptr(out2), _stream())
+    _capi.check(rc, "lgc_mark_mapk")
+    p, r = out2.cpu().tolist()
+    return p, r, per_user

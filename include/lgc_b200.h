@@ -268,6 +268,15 @@ typedef struct {
 size_t lgc_score_topk_workspace_bytes(int64_t n_users, int64_t n_items, int d, int k);
 int lgc_score_topk(const lgc_score_topk_args* args, void* stream);
 
+/* ------------------------------------------------------------------ MARK_MAPK (src/lightgcn.py:184-189)
+ * Mean precision@k and recall@k over the evaluated users: overlap = |set(held) & set(top-k)|,
+ * recall = overlap / len(held list), precision = overlap / k. held_ptr [n_users+1] / held_items:
+ * CSR of the held-out purchases (row i belongs to the user of topk row i), un-offset item ids.
+ * per_user (device, float [n_users, 2]) receives {precision, recall}; out2 (device, double[2])
+ * the two means. */
+int lgc_mark_mapk(int64_t n_users, int k, const int64_t* topk_items, const int64_t* held_ptr,
+                  const int64_t* held_items, float* per_user, double* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,3 +359,43 @@ def test_sharded_trainer_single_rank_equals_fused(dim, layers, mode):
     with torch.no_grad():
         ef = mf.get_embedding(eig, ewg).cpu()
     assert rel(sharded.embedding().cpu(), ef) < 5e-4
+
+
+# --------------------------------------------------------------------------- checkpoint wire format
+def test_checkpoint_roundtrip_in_the_reference_format(tmp_path):
+    """`save_model` writes the reference's dict (src/utils_v2.py:212-230) with a LOGICAL [N, d]
+    table although d = 90 is stored padded; resuming from it continues like the uninterrupted run
+    (to rounding), and torch.optim.Adam accepts the optimizer state."""
+    from gnn_ecommerce_b200 import FusedBPRTrainer, load_model, save_model
+    g = synth.make_graph(2000, 300, 20_000, seed=17)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    eig, ewg = ei.to(DEV), ew.to(DEV)
+    torch.manual_seed(1)
+    init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, 90)).numpy()
+    model = _model(g.num_nodes, 90, 3, init)
+    trainer = FusedBPRTrainer(model, lr=LR)
+    pl = synth.purchase_lists(g)
+    rng = np.random.default_rng(8)
+    batches = [tuple(torch.from_numpy(x).to(DEV) for x in synth.sample_triples(pl, 128, g.n_users, g.n_items, rng))
+               for _ in range(4)]
+    for b in batches[:2]:
+        trainer.step(eig, ewg, *b, DECAY)
+    path = str(tmp_path / "LightGCN_best.pt")
+    save_model(path, model, trainer, 0.1, 0.2, epoch=3, hyperparams={"latent_dim": 90, "n_layers": 3})
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"timestamp", "epoch", "model_state_dict", "optimizer_state_dict", "precision", "recall",
+                       "hyperparams"}
+    assert list(ck["model_state_dict"]) == ["alpha", "embedding.weight"]
+    assert ck["model_state_dict"]["embedding.weight"].shape == (g.num_nodes, 90)
+    ref_param = torch.nn.Parameter(ck["model_state_dict"]["embedding.weight"].clone())
+    torch.optim.Adam([ref_param], LR).load_state_dict(ck["optimizer_state_dict"])      # torch accepts it
+    model2, trainer2, _ = load_model(path, DEV)
+    assert trainer2.step_count == 2
+    for b in batches[2:]:
+        a = trainer.step(eig, ewg, *b, DECAY).cpu()
+        c = trainer2.step(eig, ewg, *b, DECAY).cpu()
+        # duplicates inside a batch meet in float atomics, so two runs agree to rounding, not bit for bit;
+        # a resume that lost the moments or the step count would be off by ~lr per weight.
+        assert torch.allclose(a, c, rtol=1e-5, atol=1e-9), (a, c)
+    dw = (model.embedding.weight.detach() - model2.embedding.weight.detach()).abs().max().item()
+    assert dw < 1e-6, dw

@@ -224,3 +224,19 @@ def test_embedding_cache_is_reused_and_invalidated():
         assert calls["n"] == 2                       # the fused step itself runs inside lgc_train_step
     finally:
         ops.propagate = orig
+
+
+def test_mark_mapk_on_device_matches_the_oracle():
+    """`MARK_MAPK` semantics (reference src/lightgcn.py:184-189) on the device vs the oracle."""
+    from gnn_ecommerce_b200 import scoring
+    rng = np.random.default_rng(9)
+    n_users, n_items, k = 3000, 500, 20
+    top = np.stack([rng.choice(n_items, k, replace=False) for _ in range(n_users)]).astype(np.int64)
+    cnt = rng.integers(1, 6, n_users)
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    held = np.concatenate([rng.choice(n_items, c) for c in cnt]).astype(np.int64)      # may repeat inside a list
+    lists = [held[ptr[i]:ptr[i + 1]].tolist() for i in range(n_users)]
+    want_p, want_r = port.mark_mapk(lists, top, k)
+    p, r, per_user = scoring.mark_mapk(torch.from_numpy(top).to(DEV), torch.from_numpy(ptr), torch.from_numpy(held))
+    assert p == pytest.approx(want_p, abs=1e-7) and r == pytest.approx(want_r, abs=1e-7)
+    assert per_user.shape == (n_users, 2)
