@@ -77,6 +77,7 @@ _SIGNATURES = {
     "lgc_sample_triples_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "lgc_sample_triples": (C.c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_uint64,
                                      C.c_uint64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lgc_debug_light_phases": (C.c_int, [c_vp]),
     "lgc_mark_mapk": (C.c_int, [c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgc_score_topk_workspace_bytes": (c_sz, [c_i64, c_i64, C.c_int, C.c_int]),
     "lgc_score_topk": (C.c_int, [C.POINTER(ScoreTopkArgs), c_vp]),

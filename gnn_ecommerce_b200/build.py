@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src in _sources():
         obj = os.path.join(PKG, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("LGC_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -71,6 +71,13 @@ __device__ __forceinline__ float4 ld_f4(const float* p) {
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
+// Same load as a volatile asm: the compiler keeps a batch of these in program order (it may not
+// sink them next to their uses to save registers, which would serialise the round trips).
+__device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_f4(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
 }
@@ -87,6 +94,22 @@ __device__ __forceinline__ float4 fma4(float w, float4 x, float4 a) {
   a.z = fmaf(w, x.z, a.z);
   a.w = fmaf(w, x.w, a.w);
   return a;
+}
+// w * x + a with two packed FFMA2 (fma.rn.f32x2, sm_100): same roundings as four fmaf, half the
+// issue slots.
+__device__ __forceinline__ float4 fma4_packed(float w, float4 x, float4 a) {
+  unsigned long long ww, x0, x1, a0, a1, r0, r1;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x1) : "f"(x.z), "f"(x.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r0) : "l"(ww), "l"(x0), "l"(a0));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r1) : "l"(ww), "l"(x1), "l"(a1));
+  float4 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(r0));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(r1));
+  return r;
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);

@@ -13,6 +13,8 @@
 // The epilogue fuses what the reference runs as separate ATen passes: the running layer mean
 // `out = out + x * alpha` (src/lightgcn.py:93,97), the backward Horner add, and dense Adam.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "spmm.cuh"
 
@@ -67,10 +69,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& a, size_t off, float4 
   } else {  // EPI_ADAM
     float4 p = q.r1, m = q.r2, v = q.r3;
     const AdamScalars ad = a.adam_dev ? *a.adam_dev : a.adam;
-    adam_update(p.x, m.x, v.x, fmaf(a.scale, s.x, q.r0.x), ad);
-    adam_update(p.y, m.y, v.y, fmaf(a.scale, s.y, q.r0.y), ad);
-    adam_update(p.z, m.z, v.z, fmaf(a.scale, s.z, q.r0.z), ad);
-    adam_update(p.w, m.w, v.w, fmaf(a.scale, s.w, q.r0.w), ad);
+    const float ib = __frcp_rn(ad.bc2_sqrt);
+    adam_update_fast(p.x, m.x, v.x, fmaf(a.scale, s.x, q.r0.x), ad, ib);
+    adam_update_fast(p.y, m.y, v.y, fmaf(a.scale, s.y, q.r0.y), ad, ib);
+    adam_update_fast(p.z, m.z, v.z, fmaf(a.scale, s.z, q.r0.z), ad, ib);
+    adam_update_fast(p.w, m.w, v.w, fmaf(a.scale, s.w, q.r0.w), ad, ib);
     st_f4(a.p + off, p);
     st_f4_cs(a.m + off, m);
     st_f4_cs(a.v + off, v);
@@ -108,17 +111,20 @@ __device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s)
 
 // ---------------------------------------------------------------------------------- light rows
 // Persistent, warp-autonomous: no CTA barrier anywhere. Every warp walks its own sequence of row
-// tiles (TR consecutive rows, ~4 KB per operand). The epilogue operands of a tile (x / acc /
+// tiles (TR consecutive rows, ~2 KB per operand). The epilogue operands of a tile (x / acc /
 // addend / p, m, v rows) are CONTIGUOUS in HBM, so threads never load them: lane 0 issues
 // bulk-async copies (cp.async.bulk, the TMA engine) of whole tiles into the warp's two-stage
-// shared-memory ring, two tiles ahead; the warp meanwhile reads the tile's CSR slice and runs the
-// gathers (neighbour rows; for user rows these are item rows that live in L2) into registers, then
-// applies the epilogue in shared memory in place, and lane 0 sends the result tiles back with
-// bulk-async stores. Dozens of KB per SM are in flight without holding a register, and writes
-// leave as whole lines. Rows above `light_max` keep their shared-memory slots untouched
-// (read-modify-write operands are stored back unchanged, plain outputs are overwritten by the
-// heavy-row kernels that run after this one on the same stream).
-constexpr int kLightWarps = 4;         // warps per CTA (each fully independent)
+// shared-memory ring, two tiles ahead, plus the tile's rowptr slice and its (src, w) slice. The
+// gathers are edge-balanced (see the kernel body): the tile's edges are compacted one lane per edge
+// and split evenly over the sub-warps, products accumulate in a shared-memory sum tile, the
+// epilogue runs in shared memory in place, and lane 0 sends the result tiles back with bulk-async
+// stores. Measured (profiles/r1f_light_bottleneck.md): the kernel is bound by issued instructions,
+// not by the gather loads -- removing every gather load changes its time by 3 %.
+// Rows above `light_max` keep their shared-memory slots untouched (read-modify-write operands are
+// stored back unchanged, plain outputs are overwritten by the heavy-row kernels that run after this
+// one on the same stream).
+constexpr int kLightWarpsMax = 5;      // warps per CTA (each fully independent): see LightCfg::WARPS
+constexpr size_t kMaxDynamicSmem = 227 * 1024;   // per CTA on sm_100
 constexpr int kLightStageCap = 128;    // CSR entries of a tile staged per warp and stage
 
 template <int L, int V, int MODE>
@@ -136,8 +142,14 @@ struct LightCfg {
   static constexpr size_t stage_bytes(int nbuf) {
     return (size_t)nbuf * TILE_FLOATS * 4 + RP_INTS * 4 + 2 * CSR_INTS * 4;
   }
-  static constexpr size_t warp_bytes(int nbuf) { return 2 * stage_bytes(nbuf) + 64; }   // + 6 mbarriers
-  static constexpr size_t smem(int nbuf) { return kLightWarps * warp_bytes(nbuf) + 128; }
+  // after the ring: 6 mbarriers | row sums S [TR x LD] | carry rows C [NSUBW x LD] | row of flat edge | s_P, s_D | carry row ids | phase clocks
+  static constexpr size_t ROWID_BYTES = (size_t)kLightStageCap * 2;  // uint16 per flat edge of a pass
+  static constexpr size_t SCRATCH_BYTES =
+      (size_t)TILE_FLOATS * 4 + (size_t)NSUBW * LD * 4 + ROWID_BYTES + 2 * 33 * 4 + 8 + 32 + 64;
+  static constexpr size_t warp_bytes(int nbuf) { return 2 * stage_bytes(nbuf) + 64 + SCRATCH_BYTES; }
+  // ADAM tiles carry 4 operand streams: 2 CTAs x 5 warps fill the 227 KB, 3 CTAs x 4 warps do not fit
+  static constexpr int WARPS = MODE == EPI_ADAM ? kLightWarpsMax : 4;   // wanted; the launcher lowers it until the CTA fits
+  static constexpr size_t smem(int nbuf, int warps) { return warps * warp_bytes(nbuf) + 128; }
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -173,30 +185,68 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Diagnostics (LGC_LIGHT_PHASES=1): device counters of the light kernel's per-phase cycles.
+unsigned long long* light_phase_buffer() {
+  static unsigned long long* buf = [] {
+    unsigned long long* p = nullptr;
+    const char* e = getenv("LGC_LIGHT_PHASES");
+    if (e && atoi(e) && cudaMalloc(&p, 8 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(p, 0, 8 * sizeof(unsigned long long));
+    return p;
+  }();
+  return buf;
+}
+
 // Requires rowptr / src / w allocations padded by >= 8 elements (graph build does that): the
 // bulk copies move 16-byte-granular supersets of the slices they need.
 template <int L, int V, int MODE>
-__global__ void __launch_bounds__(32 * kLightWarps)
+__global__ void __launch_bounds__(32 * kLightWarpsMax)
 k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float* __restrict__ w,
-             const float* __restrict__ x, int num_rows, int light_max, EpiArgs args) {
+             const float* __restrict__ x, int num_rows, int light_max, unsigned long long* phases,
+             EpiArgs args) {
   using C = LightCfg<L, V, MODE>;
   constexpr int LD = C::LD, NSUBW = C::NSUBW, RPS = C::RPS, TR = C::TR, TF = C::TILE_FLOATS;
   const int NBUF = MODE == EPI_FWD_FINAL ? args.n_hist : C::NBUF;
   const size_t stage_bytes = C::stage_bytes(NBUF);
   extern __shared__ __align__(128) uint8_t smem_light[];
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* wbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_light) + 127) & ~(uintptr_t)127) +
-                   (size_t)wic * C::warp_bytes(NBUF);
+  // plain offsets from the (128-byte aligned) dynamic shared-memory base: integer round-ups here
+  // make the compiler lose the address space and emit generic LD/ST with 64-bit addresses
+  uint8_t* wbase = smem_light + (size_t)wic * C::warp_bytes(NBUF);
   auto stage_tiles = [&](int st) { return reinterpret_cast<float*>(wbase + (size_t)st * stage_bytes); };
   auto stage_rp = [&](int st) { return reinterpret_cast<int*>(stage_tiles(st) + NBUF * TF); };
   auto stage_src = [&](int st) { return stage_rp(st) + C::RP_INTS; };
   auto stage_w = [&](int st) { return reinterpret_cast<float*>(stage_src(st) + C::CSR_INTS); };
   // barriers: [0..1] operand tiles, [2..3] rowptr slice, [4..5] CSR slice (index + stage)
   const uint32_t bar0 = smem_addr(wbase + 2 * stage_bytes);
+  float* const s_sum = reinterpret_cast<float*>(wbase + 2 * stage_bytes + 64);
+  float* const s_carry = s_sum + TF;
+  uint16_t* const c_dst = reinterpret_cast<uint16_t*>(s_carry + NSUBW * LD);   // sum slot of every flat edge
+  int* const s_P = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(c_dst) + C::ROWID_BYTES);   // [33] flat-edge prefix (s_P[TR] unused)
+  int* const s_D = s_P + 33;                                            // [33] CSR position - flat position
+  int* const s_carry_row = s_D + 35;
+  // -DLGC_PHASE_CLOCKS (diagnostic build): lane 0 sums clock64() deltas per phase of the tile loop
+#ifdef LGC_PHASE_CLOCKS
+  unsigned long long* const s_phase = reinterpret_cast<unsigned long long*>(s_carry_row + 8);
+  long long t_prev = 0;
+  if (phases && lane == 0) {
+    for (int i = 0; i < 8; ++i) s_phase[i] = 0;
+    t_prev = clock64();
+  }
+#define LGC_PHASE(i)                                   \
+  if (phases && lane == 0) {                           \
+    const long long t_now = clock64();                 \
+    s_phase[i] += (unsigned long long)(t_now - t_prev); \
+    t_prev = t_now;                                    \
+  }
+#else
+#define LGC_PHASE(i)
+#endif
   const uint64_t pol = policy_evict_first();
 
   const int n_tiles = (num_rows + TR - 1) / TR;
-  const int gw = blockIdx.x * kLightWarps + wic, nw = gridDim.x * kLightWarps;
+  const int wpc = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpc + wic, nw = gridDim.x * wpc;
   const float* in0 = MODE == EPI_PLAIN ? args.addend : (MODE == EPI_FWD_INIT ? args.xrow
                     : (MODE == EPI_FWD_RMW ? args.acc : (MODE == EPI_FWD_FINAL ? args.hist[0] : args.addend)));
   const uint32_t n_in = MODE == EPI_FWD_FINAL ? (uint32_t)args.n_hist : (in0 ? 1u : 0u) + (MODE == EPI_ADAM ? 3u : 0u);
@@ -262,8 +312,6 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
     float* buf2 = buf0 + (NBUF > 2 ? 2 * TF : 0);
     float* buf3 = buf0 + (NBUF > 3 ? 3 * TF : 0);
     const int* s_rp = stage_rp(st);
-    const int* s_src = stage_src(st);
-    const float* s_w = stage_w(st);
 
     // ---- the tile's rowptr slice and (when it fits) its CSR slice: already in shared memory
     mbar_wait_parity(bar0 + 8u * (2 + st), par);
@@ -274,68 +322,142 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
       mbar_wait_parity(bar0 + 8u * (4 + st), (csr_par >> st) & 1u);
       csr_par ^= 1u << st;
     }
+    LGC_PHASE(0)
 
-    // ---- gathers: sub-warp `sw` owns tile rows sw, sw+NSUBW, ..., two rows at a time, EU edges
-    // per row and step: 2*EU*V 128-bit loads in flight per lane
-    constexpr int EU = V >= 3 ? 1 : 2;
-    float4 acc[RPS][V];
-    bool ok[RPS];
+    // ---- gathers, EDGE-balanced. One sub-warp per row made the warp wait for the longest of the
+    // tile's rows (power law) with most lanes idle, and the kernel is bound by issued instructions.
+    // Instead the tile's light edges form one flat list (exclusive prefix s_P over the rows; rows
+    // above light_max contribute nothing), handled in passes of <= kLightStageCap edges:
+    //  1. compaction, one LANE per edge: row by bisection, then (source row offset, weight,
+    //     shared-memory slot of the sum) are written over the staged CSR slice in flat order;
+    //  2. the pass is cut into NSUBW equal runs, one per sub-warp, U gathers in flight each; every
+    //     product is added to its slot. A row that began in an earlier run of the pass goes to the
+    //     sub-warp's carry slot instead, added afterwards in sub-warp order (timing-independent).
+    int n_flat;
+    unsigned okbits;
+    {
+      int dgr = 0;
+      if (lane < rows_here) dgr = s_rp[lane + 1] - s_rp[lane];
+      const bool light = lane < rows_here && dgr <= light_max;
+      okbits = __ballot_sync(0xffffffffu, light);
+      const int dl = light ? dgr : 0;
+      int incl = dl;
 #pragma unroll
-    for (int j0 = 0; j0 < RPS; j0 += 2) {
-      int beg[2], deg[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int t = (j0 + q) * NSUBW + sw;
-        ok[j0 + q] = t < rows_here;
-        beg[q] = ok[j0 + q] ? s_rp[t] : 0;
-        deg[q] = ok[j0 + q] ? s_rp[t + 1] - beg[q] : 0;
-        ok[j0 + q] = ok[j0 + q] && deg[q] <= light_max;
-        if (!ok[j0 + q]) deg[q] = 0;
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[j0 + q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int o = 1; o < TR; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
       }
-      const int dmax = max(deg[0], deg[1]);
-      for (int t = 0; t < dmax; t += EU) {
-        int sidx[2][EU]; float wv[2][EU]; float4 xv[2][EU][V];
+      n_flat = __shfl_sync(0xffffffffu, incl, TR - 1);
+      if (lane < TR) {
+        s_P[lane] = incl - dl;
+        s_D[lane] = (lane < rows_here ? s_rp[lane] : 0) - (incl - dl);   // CSR position = flat position + s_D[row]
+      }
+      for (int i = 4 * lane; i < TF + NSUBW * LD; i += 128) st_f4(s_sum + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    {
+      constexpr int U = V >= 3 ? 2 : 4;                    // gathers in flight per lane: U * V float4
+      constexpr int CAP = kLightStageCap;
+      int* const c_off = stage_src(st);                    // compacted in place: source row offset / 16 B
+      float* const c_w = stage_w(st);
+      const char* const xb = reinterpret_cast<const char*>(x) + 16 * sl;
+      char* const sum_b = reinterpret_cast<char*>(s_sum) + 16 * sl;
+      for (int base = 0; base < n_flat; base += CAP) {
+        const int cnt = min(CAP, n_flat - base);
+        const int len = (cnt + NSUBW - 1) / NSUBW;         // run length (the last runs may be shorter / empty)
+        if (lane < NSUBW) s_carry_row[lane] = -1;
+        __syncwarp();
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+          const int j = j0 + lane;
+          int off16 = 0, dst = 0;
+          float wgt = 0.f;
+          if (j < cnt) {
+            const int f = base + j;
+            int r = 0;
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+            for (int step = TR / 2; step >= 1; step >>= 1)
+              if (s_P[r + step] <= f) r += step;
+            const int e = f + s_D[r];
+            const int sidx = staged ? c_off[e - a0] : src[e];
+            wgt = staged ? c_w[e - a0] : w[e];
+            off16 = sidx * (LD / 4);
+            int q = 0;
 #pragma unroll
-          for (int u = 0; u < EU; ++u)
-            if (t + u < deg[q]) {
-              const int e = beg[q] + t + u;
-              sidx[q][u] = staged ? s_src[e - a0] : src[e];
-              wv[q][u] = staged ? s_w[e - a0] : w[e];
+            for (int k = 1; k < NSUBW; ++k) q += (j >= k * len) ? 1 : 0;
+            const bool carry = q > 0 && s_P[r] < base + q * len;   // the row began in an earlier run of this pass
+            dst = (carry ? TF + q * LD : r * LD) * 4;
+            if (carry && j == q * len) s_carry_row[q] = r;
+          }
+          __syncwarp();                                    // in place: all reads of the batch before its writes
+          if (j < cnt) {
+            c_off[j] = off16;
+            c_w[j] = wgt;
+            c_dst[j] = (uint16_t)dst;
+          }
+        }
+        __syncwarp();
+        const int jb = sw * len, je = min(jb + len, cnt);
+        const int j_last = max(je, 1) - 1;                 // positions past the run's end: reloaded, never stored
+        const int n_steps = (len + U - 1) / U;             // same for every sub-warp
+        for (int it = 0, ju = jb; it < n_steps; ++it, ju += U) {
+          int dsto[U]; float wv[U]; float4 xv[U][V];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = min(ju + u, j_last);
+            const float* xr = reinterpret_cast<const float*>(xb + (size_t)(unsigned)c_off[j] * 16);
+            wv[u] = c_w[j];
+            dsto[u] = c_dst[j];
+#pragma unroll
+            for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+          }
+          // Scheduling fence. ptxas sinks each gather next to its use (one exposed round trip per
+          // edge) and drops warp barriers in converged code, so the first shared-memory address is made
+          // to depend on the last word of every gather: min() with a value >= 0xffff0000 never changes
+          // the 16-bit slot offset, but the loads must all be in flight before the first use.
+          {
+            unsigned dep = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v) dep |= __float_as_uint(xv[u][v].w);
+            asm("{\n.reg .u32 t;\nor.b32 t, %1, 0xffff0000;\nmin.u32 %0, %0, t;\n}" : "+r"(dsto[0]) : "r"(dep));   // opaque to the optimiser
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {                    // edge order kept per row
+            float* dst = reinterpret_cast<float*>(sum_b + dsto[u]);
+            const bool valid = ju + u < je;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float4 t = fma4_packed(wv[u], xv[u][v], ld_f4(dst + 4 * L * v));
+              if (valid) st_f4(dst + 4 * L * v, t);
             }
+          }
+        }
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int u = 0; u < EU; ++u)
-            if (t + u < deg[q]) {
-              const float* xr = x + (size_t)sidx[q][u] * LD + 4 * sl;
-#pragma unroll
-              for (int v = 0; v < V; ++v) xv[q][u][v] = ldg_f4(xr + 4 * L * v);
+        for (int q = 1; q < NSUBW; ++q) {                  // carries, in sub-warp order; slots cleared for the next pass
+          const int cr = s_carry_row[q];
+          if (cr >= 0)
+            for (int i = 4 * lane; i < LD; i += 128) {
+              st_f4(s_sum + cr * LD + i, add4(ld_f4(s_sum + cr * LD + i), ld_f4(s_carry + q * LD + i)));
+              st_f4(s_carry + q * LD + i, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int u = 0; u < EU; ++u)         // edge order kept per row
-            if (t + u < deg[q]) {
-#pragma unroll
-              for (int v = 0; v < V; ++v) acc[j0 + q][v] = fma4(wv[q][u], xv[q][u][v], acc[j0 + q][v]);
-            }
+        }
       }
     }
+    __syncwarp();
+    LGC_PHASE(1)
 
     // ---- epilogue in shared memory (same arithmetic as epi_finish), in place
     if (n_in) mbar_wait_parity(bar0 + 8u * st, par);
+    LGC_PHASE(2)
 #pragma unroll
     for (int j = 0; j < RPS; ++j) {
-      if (!ok[j]) continue;
       const int t = j * NSUBW + sw;
+      if (!((okbits >> t) & 1u)) continue;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int off = t * LD + 4 * (sl + L * v);
-        const float4 s = acc[j][v];
+        const float4 s = ld_f4(s_sum + off);
         if (MODE == EPI_PLAIN) {
           float4 r = make_float4(args.scale * s.x, args.scale * s.y, args.scale * s.z, args.scale * s.w);
           if (args.addend) {
@@ -369,10 +491,11 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
           const float4 z = ld_f4(buf0 + off);
           float4 p = ld_f4(buf1 + off), m = ld_f4(buf2 + off), vv = ld_f4(buf3 + off);
           const AdamScalars ad = args.adam_dev ? *args.adam_dev : args.adam;
-          adam_update(p.x, m.x, vv.x, fmaf(args.scale, s.x, z.x), ad);
-          adam_update(p.y, m.y, vv.y, fmaf(args.scale, s.y, z.y), ad);
-          adam_update(p.z, m.z, vv.z, fmaf(args.scale, s.z, z.z), ad);
-          adam_update(p.w, m.w, vv.w, fmaf(args.scale, s.w, z.w), ad);
+          const float ib = __frcp_rn(ad.bc2_sqrt);
+          adam_update_fast(p.x, m.x, vv.x, fmaf(args.scale, s.x, z.x), ad, ib);
+          adam_update_fast(p.y, m.y, vv.y, fmaf(args.scale, s.y, z.y), ad, ib);
+          adam_update_fast(p.z, m.z, vv.z, fmaf(args.scale, s.z, z.z), ad, ib);
+          adam_update_fast(p.w, m.w, vv.w, fmaf(args.scale, s.w, z.w), ad, ib);
           st_f4(buf1 + off, p);
           st_f4(buf2 + off, m);
           st_f4(buf3 + off, vv);
@@ -383,6 +506,7 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
     // ---- result tiles: shared memory -> HBM, asynchronously; then refill this ring stage
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
+    LGC_PHASE(3)
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)rows_here * LD * 4;
       const size_t goff = (size_t)row0 * LD;
@@ -402,7 +526,16 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
       request_tile(tile + 2 * nw, st);
     }
     __syncwarp();
+    LGC_PHASE(4)
+#ifdef LGC_PHASE_CLOCKS
+    if (phases && lane == 0) s_phase[5] += 1;
+#endif
   }
+#ifdef LGC_PHASE_CLOCKS
+  if (phases && lane == 0)
+    for (int i = 0; i < 6; ++i) atomicAdd(phases + i, s_phase[i]);
+#endif
+#undef LGC_PHASE
 }
 
 // ---------------------------------------------------------------------------------- heavy rows
@@ -574,7 +707,13 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   using LC = LightCfg<LL, LV, MODE>;
   {
     const int nbuf = MODE == EPI_FWD_FINAL ? a.n_hist : LC::NBUF;
-    const size_t smem = LC::smem(nbuf);
+    int warps = LC::WARPS;
+    while (warps > 1 && LC::smem(nbuf, warps) > kMaxDynamicSmem) --warps;
+    const size_t smem = LC::smem(nbuf, warps);
+    if (smem > kMaxDynamicSmem) {
+      set_error("row width x operand tiles do not fit in shared memory (ld=" + std::to_string(LC::LD) + ")");
+      return LGC_ERR_UNSUPPORTED;
+    }
     static int grid_light[kMaxHist + 1] = {};   // per instantiation and buffer count: SMs x resident CTAs
     static size_t smem_set = 0;
     if (smem > smem_set) {
@@ -584,15 +723,15 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
     }
     if (!grid_light[nbuf]) {
       int occ = 0;
-      LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_light<LL, LV, MODE>, 32 * kLightWarps,
-                                                             smem));
+      LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_light<LL, LV, MODE>, 32 * warps, smem));
       grid_light[nbuf] = kNumSMs * (occ > 0 ? occ : 1);
     }
     const int n_tiles = (int)ceil_div(n, LC::TR);
-    const int grid = (int)std::min<int64_t>(grid_light[nbuf], ceil_div(n_tiles, kLightWarps));
+    const int grid = (int)std::min<int64_t>(grid_light[nbuf], ceil_div(n_tiles, warps));
     ProfScope ps(PROF_LIGHT + (MODE & 3), st);
-    k_spmm_light<LL, LV, MODE><<<grid, 32 * kLightWarps, smem, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
-                                                                    g->light_max_degree, a);
+    k_spmm_light<LL, LV, MODE><<<grid, 32 * warps, smem, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
+                                                                    g->light_max_degree,
+                                                                    light_phase_buffer(), a);
   }
   LGC_LAUNCH_CHECK();
   if (g->num_chunks > 0) {
@@ -783,4 +922,17 @@ extern "C" int lgc_propagate(const lgc_graph_t* g, int ld, int num_layers, const
   for (int l = 0; l + 1 < num_layers; ++l) xs[l] = ws + (size_t)l * t;
   float* partials = ws + (size_t)(num_layers - 1) * t;
   return propagate_chain(g, ld, num_layers, h_alpha, x0, out, xs, partials, st);
+}
+
+// Diagnostics: cycles per phase of k_spmm_light since the last call (needs LGC_LIGHT_PHASES=1 in the
+// environment; otherwise all zeros). out[0..4] = wait CSR | gathers | wait operands | epilogue |
+// lane-0 store/refill, out[5] = warp-tiles.
+extern "C" int lgc_debug_light_phases(unsigned long long* out8) {
+  unsigned long long* buf = light_phase_buffer();
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (!buf) return LGC_OK;
+  LGC_CUDA(cudaDeviceSynchronize());
+  LGC_CUDA(cudaMemcpy(out8, buf, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  LGC_CUDA(cudaMemset(buf, 0, 8 * sizeof(unsigned long long)));
+  return LGC_OK;
 }

@@ -277,6 +277,12 @@ int lgc_score_topk(const lgc_score_topk_args* args, void* stream);
 int lgc_mark_mapk(int64_t n_users, int k, const int64_t* topk_items, const int64_t* held_ptr,
                   const int64_t* held_items, float* per_user, double* out2, void* stream);
 
+/* Diagnostics: clock64() cycles per phase of the light-row SpMM kernel since the last call, summed
+ * over warps (only when the process runs with LGC_LIGHT_PHASES=1; zeros otherwise). out8[0..4] =
+ * wait for CSR slices | gathers | wait for operand tiles | epilogue | store + refill; out8[5] =
+ * warp-tiles. Synchronises the device. */
+int lgc_debug_light_phases(unsigned long long* out8);
+
 #ifdef __cplusplus
 }
 #endif
