@@ -539,25 +539,31 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
 }
 
 // ---------------------------------------------------------------------------------- heavy rows
-// Item rows: every chunk (<= 256 edges of one row) is one warp's work item. The gathers are random
-// 256-byte reads of a table far larger than L2, i.e. pure latency: the version that gathered into
-// registers (8 loads, wait, 8 FMAs, ...) sat at 21 long-scoreboard stalls per issued instruction.
-// Here the neighbour rows are copied with cp.async (LDGSTS: no destination register, no in-order
-// wait) into a per-warp shared-memory ring of kHeavyStages groups of R rows, kHeavyStages-1 groups
-// ahead of the FMAs, so ~12 KB per warp are in flight all the time.
+// Hub rows (mostly items): every chunk (<= 256 source-sorted edges of one row) is a work item; a
+// warp walks its chunks (c, c + #warps, ...) as ONE continuous stream of groups of R edges, so the
+// copy pipeline never drains between chunks. Neighbour rows are copied with cp.async (LDGSTS: no
+// destination register, no in-order wait) into a per-warp shared-memory ring of kHeavyStages
+// groups, kHeavyStages-1 groups ahead of the FMAs (~12 KB per warp in flight). The kernel is bound
+// by issued instructions (profiles/r1f_light_bottleneck.md), hence: one coalesced load of a
+// group's (src, w) by R lanes and shuffles instead of per-edge broadcast loads, weights transposed
+// in shared memory so that a stream reads its EPL weights as vectors, packed FFMA2, and no padding
+// guards (the ring is zeroed once; rows that are not copied keep finite data and get weight 0).
 constexpr int kHeavyWarps = 4;         // warps per CTA (independent: no CTA barrier)
 constexpr int kHeavyStages = 4;
+constexpr int kHeavyQueue = 8;         // chunk descriptors between the fetch cursor and the FMAs
 
 template <int L, int V>
 struct HeavyCfg {
   static constexpr int LD = 4 * L * V;
   static constexpr int RPW = 32 / L;                                   // edge streams per warp
-  static constexpr int R0 = 4096 / (LD * 4);                           // ~4 KB of rows per group
-  static constexpr int R = R0 < 2 * RPW ? 2 * RPW : (R0 / RPW * RPW);  // rows per group (multiple of RPW)
+  static constexpr int R0 = 4096 / (LD * 4) > 32 ? 32 : 4096 / (LD * 4);   // ~4 KB of rows per group, <= one lane per edge
+  static constexpr int RMIN = 2 * RPW > 32 ? 32 : 2 * RPW;
+  static constexpr int R = R0 / RPW * RPW < RMIN ? RMIN : R0 / RPW * RPW;   // rows per group (multiple of RPW)
   static constexpr int EPL = R / RPW;                                  // edges per lane-stream and group
-  static constexpr size_t GROUP_BYTES = (size_t)R * LD * 4 + (size_t)R * 4;   // rows + their weights
-  static constexpr size_t WARP_BYTES = kHeavyStages * ((GROUP_BYTES + 15) / 16 * 16);
+  static constexpr size_t GROUP_BYTES = ((size_t)R * LD * 4 + (size_t)R * 4 + 15) / 16 * 16;   // rows + their weights
+  static constexpr size_t WARP_BYTES = kHeavyStages * GROUP_BYTES + kHeavyQueue * 16;
   static constexpr size_t SMEM = kHeavyWarps * WARP_BYTES + 16;
+  static_assert(R <= 32, "one lane per edge of a group");
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -575,73 +581,92 @@ k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks, const int32_t* __r
   extern __shared__ __align__(16) uint8_t smem_heavy[];
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wbase = smem_heavy + (size_t)wic * C::WARP_BYTES;
-  auto slot_rows = [&](int sl_) { return reinterpret_cast<float*>(wbase + (size_t)sl_ * (C::WARP_BYTES / S)); };
-  auto slot_w = [&](int sl_) { return slot_rows(sl_) + R * LD; };
+  auto slot_rows = [&](int sl_) { return reinterpret_cast<float*>(wbase + (size_t)sl_ * C::GROUP_BYTES); };
+  auto slot_w = [&](int sl_) { return slot_rows(sl_) + R * LD; };       // transposed: [stream][EPL]
+  int4* const queue = reinterpret_cast<int4*>(wbase + (size_t)S * C::GROUP_BYTES);
   const int sub = lane / L, sl = lane % L;
-  // persistent: chunk c goes to warp c mod #warps (every warp gets the same mix of hub and short chunks)
   const int n_warps = gridDim.x * kHeavyWarps;
-  for (int c_idx = blockIdx.x * kHeavyWarps + wic; c_idx < num_chunks; c_idx += n_warps) {
-    const int4 c = chunks[c_idx];
-    const int row = c.x, beg = c.y, end = c.z, slot = c.w;
-    const int n_groups = (end - beg + R - 1) / R;
+  const int first = blockIdx.x * kHeavyWarps + wic;
+  if (first >= num_chunks) return;
 
-    // stream `sub` of group g takes edges beg + g*R + i*RPW + sub, i < EPL
-    int idx[EPL]; float wgt[EPL];
-    auto load_idx = [&](int g) {
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) {
-        const int e = beg + g * R + i * RPW + sub;
-        idx[i] = -1; wgt[i] = 0.f;
-        if (g < n_groups && e < end) { idx[i] = src[e]; wgt[i] = w[e]; }
-      }
-    };
-    auto issue = [&](int g) {                       // uses idx/wgt loaded for group g
-      if (g < n_groups) {
-        float* rows = slot_rows(g % S);
-        float* ws = slot_w(g % S);
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-          const int r = i * RPW + sub;
-          if (idx[i] >= 0) {
-            const float* xr = x + (size_t)idx[i] * LD + 4 * sl;
-#pragma unroll
-            for (int v = 0; v < V; ++v) cp_async16(rows + r * LD + 4 * (sl + L * v), xr + 4 * L * v);
-          }
-          if (sl == 0) ws[r] = wgt[i];             // 0 for the padding of the last group
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");   // one group per step, empty or not
-    };
+  for (int i = 16 * lane; i < (int)(S * C::GROUP_BYTES); i += 512)       // ring: finite data everywhere
+    *reinterpret_cast<float4*>(wbase + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float4 acc[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();                                   // the previous chunk's last reads of the ring are done
-#pragma unroll 1
-    for (int g = 0; g < S - 1; ++g) { load_idx(g); issue(g); }
-    load_idx(S - 1);
-#pragma unroll 1
-    for (int g = 0; g < n_groups; ++g) {
-      issue(g + S - 1);                             // into the slot consumed in the previous iteration
-      load_idx(g + S);                              // indices one group ahead of their issue
-      asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
-      __syncwarp();                                 // every lane's copies of group g have landed
-      const float* rows = slot_rows(g % S);
-      const float* ws = slot_w(g % S);
-      const int n_here = min(R, end - beg - g * R);
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) {
-        const int r = i * RPW + sub;
-        if (r < n_here) {
-          const float wv = ws[r];
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = fma4(wv, ld_f4(rows + r * LD + 4 * (sl + L * v)), acc[v]);
-        }
+  // ---- fetch cursor: group (f_k, f_g) of the warp's chunk sequence; `nxt` = descriptor of chunk f_k + 1
+  int f_k = 0, f_g = 0, f_beg, f_end, f_ng;
+  bool f_valid = true;
+  int4 nxt;
+  {
+    const int4 c = chunks[first];
+    f_beg = c.y; f_end = c.z; f_ng = (c.z - c.y + R - 1) / R;
+    if (lane == 0) queue[0] = c;
+    const int c1 = first + n_warps;
+    nxt = c1 < num_chunks ? chunks[c1] : make_int4(0, 0, 0, 0);
+  }
+  int my_idx, my_w_bits;                            // this lane's edge of the group fetched last
+  auto fetch = [&]() {
+    my_idx = -1; my_w_bits = 0;
+    if (!f_valid) return;
+    const int e = f_beg + f_g * R + lane;
+    if (lane < R && e < f_end) { my_idx = src[e]; my_w_bits = __float_as_int(w[e]); }
+    if (++f_g == f_ng) {                            // next chunk: its descriptor is already in registers
+      ++f_k; f_g = 0;
+      const int c_idx = first + f_k * n_warps;
+      f_valid = c_idx < num_chunks;
+      if (f_valid) {
+        f_beg = nxt.y; f_end = nxt.z; f_ng = (nxt.z - nxt.y + R - 1) / R;
+        if (lane == 0) queue[f_k % kHeavyQueue] = nxt;
+        const int c2 = c_idx + n_warps;
+        if (c2 < num_chunks) nxt = chunks[c2];
       }
-      __syncwarp();                                 // slot g % S may be refilled
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // combine the RPW edge streams (fixed order: deterministic)
+  };
+  auto issue = [&](int slot_) {                     // the group held in (my_idx, my_w_bits) -> ring slot
+    float* rows = slot_rows(slot_);
+    if (lane < R) slot_w(slot_)[(lane % RPW) * EPL + lane / RPW] = __int_as_float(my_w_bits);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int r = i * RPW + sub;
+      const int idx = __shfl_sync(0xffffffffu, my_idx, r);
+      if (idx >= 0) {
+        const float* xr = x + (size_t)idx * LD + 4 * sl;
+#pragma unroll
+        for (int v = 0; v < V; ++v) cp_async16(rows + r * LD + 4 * (sl + L * v), xr + 4 * L * v);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per step, empty or not
+  };
+
+  __syncwarp();
+#pragma unroll 1
+  for (int g = 0; g < S - 1; ++g) { fetch(); issue(g); }
+  fetch();
+
+  // ---- consumer: group (c_k, c_g)
+  int c_k = 0, c_g = 0;
+  int4 cur = chunks[first];
+  int c_ng = (cur.z - cur.y + R - 1) / R;
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int t = 0;; ++t) {
+    issue((t + S - 1) % S);                         // into the slot consumed in the previous iteration
+    fetch();                                        // indices one group ahead of their issue
+    asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+    __syncwarp();                                   // every lane's copies of group t have landed
+    const float* rows = slot_rows(t % S);
+    const float* ws = slot_w(t % S) + sub * EPL;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int r = i * RPW + sub;
+      const float wv = ws[i];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = fma4_packed(wv, ld_f4(rows + r * LD + 4 * (sl + L * v)), acc[v]);
+    }
+    __syncwarp();                                   // slot t % S may be refilled
+    if (++c_g < c_ng) continue;
+    // ---- end of a chunk: combine the RPW edge streams (fixed order: deterministic), write, next chunk
 #pragma unroll
     for (int o = L; o < 32; o <<= 1) {
 #pragma unroll
@@ -652,17 +677,25 @@ k_spmm_heavy(const int4* __restrict__ chunks, int num_chunks, const int32_t* __r
         acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
       }
     }
-    if (sub != 0) continue;
-    if (slot >= 0) {
-      float* pr = partials + (size_t)slot * LD + 4 * sl;
+    if (sub == 0) {
+      if (cur.w >= 0) {
+        float* pr = partials + (size_t)cur.w * LD + 4 * sl;
 #pragma unroll
-      for (int v = 0; v < V; ++v) st_f4(pr + 4 * L * v, acc[v]);
-    } else {
-      const size_t off = (size_t)row * LD + 4 * sl;
+        for (int v = 0; v < V; ++v) st_f4(pr + 4 * L * v, acc[v]);
+      } else {
+        const size_t off = (size_t)cur.x * LD + 4 * sl;
 #pragma unroll
-      for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+        for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
+      }
     }
+    ++c_k; c_g = 0;
+    if (first + c_k * n_warps >= num_chunks) break;
+    cur = queue[c_k % kHeavyQueue];
+    c_ng = (cur.z - cur.y + R - 1) / R;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // One CTA per split row: 256/L streams add the row's partials (fixed assignment and a fixed
