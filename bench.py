@@ -138,9 +138,9 @@ def algorithmic_bytes(g, dim_ld: int, layers: int, nnz: int):
     return {"I": idx, "T": t, "B_prop": b_prop, "step": 2 * b_prop + 7 * t}
 
 
-def light_kernel_bytes(g, graph, ld: int):
+def light_kernel_bytes(g, graph, ld: int, layers: int = 3):
     """Algorithmic bytes of ONE launch of the dominant kernel (k_spmm_light, the sub-warp-per-row
-    pass over rows with in-degree <= 32), averaged over the 6 launches of a K=3 step:
+    pass over rows with in-degree <= 32), averaged over the 2K launches of a K-layer step:
     indices + weights of the light rows' edges, each distinct gathered source row once, rowptr,
     plus the epilogue traffic of the light rows (mode dependent)."""
     a = graph.arrays()
@@ -154,11 +154,12 @@ def light_kernel_bytes(g, graph, ld: int):
     rb = ld * 4
     n_light = int(light.sum())
     gather = e_light * 8 + (g.num_nodes + 1) * 4 + distinct_src * rb
-    per_mode = {"fwd_init": 3 * rb, "fwd_rmw_store": 3 * rb, "fwd_rmw_last": 2 * rb,
-                "bwd_plain": 2 * rb, "bwd_adam": 7 * rb}
-    # K = 3 step: fwd_init, fwd_rmw(store), fwd_rmw(last), bwd_plain x2, bwd_adam
-    epi = (per_mode["fwd_init"] + per_mode["fwd_rmw_store"] + per_mode["fwd_rmw_last"]
-           + 2 * per_mode["bwd_plain"] + per_mode["bwd_adam"]) / 6.0
+    # one step (csrc/train_step.cu): forward K-1 x PLAIN (1 row stream each: the layer table written) and
+    # FWD_FINAL (K hist tables read + out written); backward K-1 x PLAIN + addend (read + write) and ADAM
+    # (addend, p, m, v read; p, m, v written)
+    k = max(1, layers)
+    streams = [1] * (k - 1) + [k + 1] + [2] * (k - 1) + [7]
+    epi = rb * sum(streams) / float(len(streams))
     return {"bytes_per_launch": gather + n_light * epi, "light_rows": n_light,
             "light_edges": e_light, "distinct_sources": distinct_src}
 
@@ -395,7 +396,7 @@ def main():
                 "bpr": ms_arr[12] / args.steps}
     step_gbs = alg["step"] / (ms_step * 1e-3) / 1e9
     if world == 1:
-        lk = light_kernel_bytes(g, graph, ld)
+        lk = light_kernel_bytes(g, graph, ld, layers)
         achieved = lk["bytes_per_launch"] / (light_avg_ms * 1e-3) / 1e9
         traffic = None
         prof_json = os.path.join(ROOT, "profiles", "ncu_light_traffic.json")

@@ -71,11 +71,11 @@ __device__ __forceinline__ float4 ld_f4(const float* p) {
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
-// Same load as a volatile asm: the compiler keeps a batch of these in program order (it may not
-// sink them next to their uses to save registers, which would serialise the round trips).
-__device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
+// read-only 128-bit load as plain PTX (inside hot loops __ldg made ptxas rebuild a memory descriptor,
+// two R2UR, for every load)
+__device__ __forceinline__ float4 ldg_f4_ptx(const float* p) {
   float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_f4(float* p, float4 v) {

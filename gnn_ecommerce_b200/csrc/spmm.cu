@@ -352,23 +352,31 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
         s_P[lane] = incl - dl;
         s_D[lane] = (lane < rows_here ? s_rp[lane] : 0) - (incl - dl);   // CSR position = flat position + s_D[row]
       }
-      for (int i = 4 * lane; i < TF + NSUBW * LD; i += 128) st_f4(s_sum + i, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+      for (int i = 0; i < (TF + NSUBW * LD) / 128; ++i)     // sums + carry slots (both multiples of 128 floats)
+        st_f4(s_sum + 128 * i + 4 * lane, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     {
-      constexpr int U = V >= 3 ? 2 : 4;                    // gathers in flight per lane: U * V float4
-      constexpr int CAP = kLightStageCap;
+      constexpr int U0 = V >= 3 ? 2 : 4;                   // gathers in flight per lane: U * V float4
+      constexpr int U = NSUBW * U0 > 32 ? 32 / NSUBW : U0;
+      constexpr int CAP = kLightStageCap - 32;             // flat edges per pass; a multiple of NSUBW * U
+      static_assert(CAP % (NSUBW * U) == 0, "full passes need no padding");
       int* const c_off = stage_src(st);                    // compacted in place: source row offset / 16 B
       float* const c_w = stage_w(st);
-      const char* const xb = reinterpret_cast<const char*>(x) + 16 * sl;
+      const char* xb = reinterpret_cast<const char*>(x) + 16 * sl;
+      asm("" : "+l"(xb));                                  // one 64-bit register pair: IMAD.WIDE adds it directly
       char* const sum_b = reinterpret_cast<char*>(s_sum) + 16 * sl;
       for (int base = 0; base < n_flat; base += CAP) {
         const int cnt = min(CAP, n_flat - base);
-        const int len = (cnt + NSUBW - 1) / NSUBW;         // run length (the last runs may be shorter / empty)
+        // run length per sub-warp, a multiple of U: the slots past the pass's last edge are padding
+        // (weight 0, source row 0, sum slot = the unused carry slot of sub-warp 0)
+        const int len = ((cnt + NSUBW - 1) / NSUBW + U - 1) / U * U;
+        const int n_slots = NSUBW * len;
         if (lane < NSUBW) s_carry_row[lane] = -1;
         __syncwarp();
-        for (int j0 = 0; j0 < cnt; j0 += 32) {
+        for (int j0 = 0; j0 < n_slots; j0 += 32) {
           const int j = j0 + lane;
-          int off16 = 0, dst = 0;
+          int off16 = 0, dst = TF * 4;
           float wgt = 0.f;
           if (j < cnt) {
             const int f = base + j;
@@ -388,26 +396,23 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
             if (carry && j == q * len) s_carry_row[q] = r;
           }
           __syncwarp();                                    // in place: all reads of the batch before its writes
-          if (j < cnt) {
+          if (j < n_slots) {
             c_off[j] = off16;
             c_w[j] = wgt;
             c_dst[j] = (uint16_t)dst;
           }
         }
         __syncwarp();
-        const int jb = sw * len, je = min(jb + len, cnt);
-        const int j_last = max(je, 1) - 1;                 // positions past the run's end: reloaded, never stored
-        const int n_steps = (len + U - 1) / U;             // same for every sub-warp
-        for (int it = 0, ju = jb; it < n_steps; ++it, ju += U) {
+        const int n_steps = len / U;                       // same for every sub-warp
+        for (int it = 0, j = sw * len; it < n_steps; ++it, j += U) {
           int dsto[U]; float wv[U]; float4 xv[U][V];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int j = min(ju + u, j_last);
-            const float* xr = reinterpret_cast<const float*>(xb + (size_t)(unsigned)c_off[j] * 16);
-            wv[u] = c_w[j];
-            dsto[u] = c_dst[j];
+            const float* xr = reinterpret_cast<const float*>(xb + (size_t)(unsigned)c_off[j + u] * 16);
+            wv[u] = c_w[j + u];
+            dsto[u] = c_dst[j + u];
 #pragma unroll
-            for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4(xr + 4 * L * v);
+            for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4_ptx(xr + 4 * L * v);
           }
           // Scheduling fence. ptxas sinks each gather next to its use (one exposed round trip per
           // edge) and drops warp barriers in converged code, so the first shared-memory address is made
@@ -424,12 +429,9 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
 #pragma unroll
           for (int u = 0; u < U; ++u) {                    // edge order kept per row
             float* dst = reinterpret_cast<float*>(sum_b + dsto[u]);
-            const bool valid = ju + u < je;
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const float4 t = fma4_packed(wv[u], xv[u][v], ld_f4(dst + 4 * L * v));
-              if (valid) st_f4(dst + 4 * L * v, t);
-            }
+            for (int v = 0; v < V; ++v)
+              st_f4(dst + 4 * L * v, fma4_packed(wv[u], xv[u][v], ld_f4(dst + 4 * L * v)));
           }
         }
         __syncwarp();
@@ -508,17 +510,36 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
     __syncwarp();
     LGC_PHASE(3)
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)rows_here * LD * 4;
-      const size_t goff = (size_t)row0 * LD;
-      if (MODE == EPI_PLAIN) {
-        bulk_store(args.y + goff, buf0, bytes, pol);
-      } else if (MODE == EPI_ADAM) {
-        bulk_store(args.p + goff, buf1, bytes, pol);
-        bulk_store(args.m + goff, buf2, bytes, pol);
-        bulk_store(args.v + goff, buf3, bytes, pol);
+      // Only rows this kernel owns are written: the hub rows of the tile belong to the heavy-row
+      // kernels, which may run CONCURRENTLY on a second stream. A tile without hub rows (the common
+      // case) leaves as one copy per output table, otherwise one copy per run of light rows.
+      auto store_rows = [&](int a, int n) {
+        const uint32_t bytes = (uint32_t)n * LD * 4;
+        const size_t goff = (size_t)(row0 + a) * LD;
+        const int so = a * LD;
+        if (MODE == EPI_PLAIN) {
+          bulk_store(args.y + goff, buf0 + so, bytes, pol);
+        } else if (MODE == EPI_ADAM) {
+          bulk_store(args.p + goff, buf1 + so, bytes, pol);
+          bulk_store(args.m + goff, buf2 + so, bytes, pol);
+          bulk_store(args.v + goff, buf3 + so, bytes, pol);
+        } else {
+          bulk_store(args.acc + goff, buf0 + so, bytes, pol);
+          if (args.y) bulk_store(args.y + goff, buf1 + so, bytes, pol);
+        }
+      };
+      const unsigned full = rows_here >= 32 ? 0xffffffffu : ((1u << rows_here) - 1u);
+      if (okbits == full) {
+        store_rows(0, rows_here);
       } else {
-        bulk_store(args.acc + goff, buf0, bytes, pol);
-        if (args.y) bulk_store(args.y + goff, buf1, bytes, pol);
+        unsigned todo = okbits;
+        while (todo) {
+          const int a = __ffs(todo) - 1;
+          const unsigned rest = ~(todo >> a);
+          const int n = rest ? __ffs(rest) - 1 : 32 - a;
+          todo = (n >= 32) ? 0u : (todo & ~(((1u << n) - 1u) << a));
+          store_rows(a, n);
+        }
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       request_csr(tile + nw, st ^ 1, k + 1);                              // next tile's CSR slice
@@ -551,12 +572,16 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
 constexpr int kHeavyWarps = 4;         // warps per CTA (independent: no CTA barrier)
 constexpr int kHeavyStages = 4;
 constexpr int kHeavyQueue = 8;         // chunk descriptors between the fetch cursor and the FMAs
+#ifndef LGC_HEAVY_GROUP_BYTES
+#define LGC_HEAVY_GROUP_BYTES 4096
+#endif
+constexpr int kHeavyGroupBytes = LGC_HEAVY_GROUP_BYTES;   // rows of one ring slot
 
 template <int L, int V>
 struct HeavyCfg {
   static constexpr int LD = 4 * L * V;
   static constexpr int RPW = 32 / L;                                   // edge streams per warp
-  static constexpr int R0 = 4096 / (LD * 4) > 32 ? 32 : 4096 / (LD * 4);   // ~4 KB of rows per group, <= one lane per edge
+  static constexpr int R0 = kHeavyGroupBytes / (LD * 4) > 32 ? 32 : kHeavyGroupBytes / (LD * 4);   // <= one lane per edge
   static constexpr int RMIN = 2 * RPW > 32 ? 32 : 2 * RPW;
   static constexpr int R = R0 / RPW * RPW < RMIN ? RMIN : R0 / RPW * RPW;   // rows per group (multiple of RPW)
   static constexpr int EPL = R / RPW;                                  // edges per lane-stream and group
@@ -731,6 +756,41 @@ __global__ void __launch_bounds__(256) k_spmm_finish(const int4* __restrict__ sp
   for (int v = 0; v < V; ++v) epilogue<MODE>(args, off + 4 * L * v, acc[v]);
 }
 
+// The light-row kernel is bound by issued instructions and leaves HBM half idle; the heavy-row
+// kernel waits on random 256-byte reads and leaves the issue slots idle. They touch disjoint rows,
+// so (except for the ADAM epilogue, whose tiles fill the shared memory) they CAN run concurrently
+// (LGC_SPMM_OVERLAP=1): heavy + finish on a side stream between a fork and a join event, with the persistent grids sized
+// so that `kHeavyCtasOverlap` heavy CTAs and the light CTAs fit one SM together. Works inside
+// stream capture (the side stream joins the capture through the events).
+#ifndef LGC_HEAVY_CTAS_OVERLAP
+#define LGC_HEAVY_CTAS_OVERLAP 1
+#endif
+constexpr int kHeavyCtasOverlap = LGC_HEAVY_CTAS_OVERLAP;
+constexpr size_t kSmemPerSM = 228 * 1024, kSmemPerCtaReserved = 1024;
+struct OverlapCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+OverlapCtx* overlap_ctx() {
+  static OverlapCtx ctx[64];
+  // Off by default: measured at c2 (profiles/r1f_light_bottleneck.md) both kernels are bound by issued
+  // instructions, so running them side by side gains nothing (3.61 vs 3.54 ms per step).
+  static const bool enabled = [] { const char* e = getenv("LGC_SPMM_OVERLAP"); return e && atoi(e) != 0; }();
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  OverlapCtx& c = ctx[dev];
+  if (!c.ok) {
+    // created on the first (eager) launch: callers that capture CUDA graphs run eager steps first
+    if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    c.ok = true;
+  }
+  return &c;
+}
+
 // L, V: row geometry of the heavy-row kernels (widest sub-warp); LL, LV: of the light-row kernel
 // (few lanes per row: more rows per warp instruction, more gathers in flight per lane)
 template <int L, int V, int LL, int LV, int MODE>
@@ -738,63 +798,78 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   const int threads = 256;
   const int64_t n = g->num_nodes;
   using LC = LightCfg<LL, LV, MODE>;
-  {
-    const int nbuf = MODE == EPI_FWD_FINAL ? a.n_hist : LC::NBUF;
-    int warps = LC::WARPS;
-    while (warps > 1 && LC::smem(nbuf, warps) > kMaxDynamicSmem) --warps;
-    const size_t smem = LC::smem(nbuf, warps);
-    if (smem > kMaxDynamicSmem) {
-      set_error("row width x operand tiles do not fit in shared memory (ld=" + std::to_string(LC::LD) + ")");
-      return LGC_ERR_UNSUPPORTED;
+  using HC = HeavyCfg<L, V>;
+  const int nbuf = MODE == EPI_FWD_FINAL ? a.n_hist : LC::NBUF;
+  int warps = LC::WARPS;
+  while (warps > 1 && LC::smem(nbuf, warps) > kMaxDynamicSmem) --warps;
+  const size_t smem = LC::smem(nbuf, warps);
+  if (smem > kMaxDynamicSmem) {
+    set_error("row width x operand tiles do not fit in shared memory (ld=" + std::to_string(LC::LD) + ")");
+    return LGC_ERR_UNSUPPORTED;
+  }
+  // light CTAs per SM that leave room for the overlapping heavy CTAs
+  const size_t heavy_need = kHeavyCtasOverlap * (HC::SMEM + kSmemPerCtaReserved);
+  const int light_cap = heavy_need < kSmemPerSM ? (int)((kSmemPerSM - heavy_need) / (smem + kSmemPerCtaReserved)) : 0;
+  OverlapCtx* ov = (MODE != EPI_ADAM && g->num_chunks > 0 && light_cap >= 1) ? overlap_ctx() : nullptr;
+  cudaStream_t hs = st;
+  if (ov) {
+    LGC_CUDA(cudaEventRecord(ov->fork, st));
+    LGC_CUDA(cudaStreamWaitEvent(ov->side, ov->fork, 0));
+    hs = ov->side;
+  }
+  // ---- heavy rows (+ the sums of split rows): launched first so that their CTAs find room
+  if (g->num_chunks > 0) {
+    static int occ_heavy = 0;            // per instantiation: resident CTAs per SM
+    if (!occ_heavy) {
+      LGC_CUDA(cudaFuncSetAttribute(k_spmm_heavy<L, V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)HC::SMEM));
+      int occ = 0;
+      LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_heavy<L, V, MODE>, 32 * kHeavyWarps,
+                                                             HC::SMEM));
+      occ_heavy = occ > 0 ? occ : 1;
     }
-    static int grid_light[kMaxHist + 1] = {};   // per instantiation and buffer count: SMs x resident CTAs
+    const int per_sm = ov ? std::min(occ_heavy, kHeavyCtasOverlap) : occ_heavy;
+    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, kHeavyWarps), (int64_t)kNumSMs * per_sm);
+    {
+      ProfScope ps(PROF_HEAVY + (MODE & 3), hs);
+      k_spmm_heavy<L, V, MODE><<<grid_heavy, 32 * kHeavyWarps, HC::SMEM, hs>>>(
+          g->chunks, (int)g->num_chunks, g->hsrc, g->hw, x, partials, a);
+    }
+    LGC_LAUNCH_CHECK();
+    if (g->num_split_rows > 0) {
+      const int grid_fin = (int)g->num_split_rows;
+      {
+        ProfScope ps(PROF_FINISH + (MODE & 3), hs);
+        k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, hs>>>(g->split_rows, (int)g->num_split_rows,
+                                                                 partials, a);
+      }
+      LGC_LAUNCH_CHECK();
+    }
+  }
+  if (ov) LGC_CUDA(cudaEventRecord(ov->join, hs));
+  // ---- light rows
+  {
+    static int occ_light[kMaxHist + 1] = {};   // per instantiation and buffer count: resident CTAs per SM
     static size_t smem_set = 0;
     if (smem > smem_set) {
       LGC_CUDA(cudaFuncSetAttribute(k_spmm_light<LL, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
       smem_set = smem;
     }
-    if (!grid_light[nbuf]) {
+    if (!occ_light[nbuf]) {
       int occ = 0;
       LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_light<LL, LV, MODE>, 32 * warps, smem));
-      grid_light[nbuf] = kNumSMs * (occ > 0 ? occ : 1);
+      occ_light[nbuf] = occ > 0 ? occ : 1;
     }
+    const int per_sm = ov ? std::min(occ_light[nbuf], light_cap) : occ_light[nbuf];
     const int n_tiles = (int)ceil_div(n, LC::TR);
-    const int grid = (int)std::min<int64_t>(grid_light[nbuf], ceil_div(n_tiles, warps));
+    const int grid = (int)std::min<int64_t>((int64_t)kNumSMs * per_sm, ceil_div(n_tiles, warps));
     ProfScope ps(PROF_LIGHT + (MODE & 3), st);
     k_spmm_light<LL, LV, MODE><<<grid, 32 * warps, smem, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
-                                                                    g->light_max_degree,
-                                                                    light_phase_buffer(), a);
+                                                                g->light_max_degree, light_phase_buffer(), a);
   }
   LGC_LAUNCH_CHECK();
-  if (g->num_chunks > 0) {
-    using HC = HeavyCfg<L, V>;
-    static int grid_heavy_max = 0;       // per instantiation: persistent grid = SMs x resident CTAs
-    if (!grid_heavy_max) {
-      LGC_CUDA(cudaFuncSetAttribute(k_spmm_heavy<L, V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)HC::SMEM));
-      int occ = 0;
-      LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_heavy<L, V, MODE>, 32 * kHeavyWarps,
-                                                             HC::SMEM));
-      grid_heavy_max = kNumSMs * (occ > 0 ? occ : 1);
-    }
-    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, kHeavyWarps), grid_heavy_max);
-    {
-      ProfScope ps(PROF_HEAVY + (MODE & 3), st);
-      k_spmm_heavy<L, V, MODE><<<grid_heavy, 32 * kHeavyWarps, HC::SMEM, st>>>(
-          g->chunks, (int)g->num_chunks, g->hsrc, g->hw, x, partials, a);
-    }
-    LGC_LAUNCH_CHECK();
-  }
-  if (g->num_split_rows > 0) {
-    const int grid_fin = (int)g->num_split_rows;
-    {
-      ProfScope ps(PROF_FINISH + (MODE & 3), st);
-      k_spmm_finish<L, V, MODE><<<grid_fin, threads, 0, st>>>(g->split_rows, (int)g->num_split_rows,
-                                                               partials, a);
-    }
-    LGC_LAUNCH_CHECK();
-  }
+  if (ov) LGC_CUDA(cudaStreamWaitEvent(st, ov->join, 0));
   return LGC_OK;
 }
 
