@@ -404,6 +404,13 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
         }
         __syncwarp();
         const int n_steps = len / U;                       // same for every sub-warp
+        // The running sum of the current slot lives in registers: shared memory is read when the
+        // slot changes and written when it is left (the kernel is bound by shared-memory wavefronts:
+        // a read-modify-write per edge cost 16 of them, rows have ~3 edges).
+        int cur = -1;
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int it = 0, j = sw * len; it < n_steps; ++it, j += U) {
           int dsto[U]; float wv[U]; float4 xv[U][V];
 #pragma unroll
@@ -415,9 +422,9 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
             for (int v = 0; v < V; ++v) xv[u][v] = ldg_f4_ptx(xr + 4 * L * v);
           }
           // Scheduling fence. ptxas sinks each gather next to its use (one exposed round trip per
-          // edge) and drops warp barriers in converged code, so the first shared-memory address is made
-          // to depend on the last word of every gather: min() with a value >= 0xffff0000 never changes
-          // the 16-bit slot offset, but the loads must all be in flight before the first use.
+          // edge) and drops warp barriers in converged code, so the first slot offset is made to
+          // depend on the last word of every gather: min() with a value >= 0xffff0000 never changes
+          // the 16-bit offset, but the loads must all be in flight before the first use.
           {
             unsigned dep = 0;
 #pragma unroll
@@ -428,11 +435,22 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {                    // edge order kept per row
-            float* dst = reinterpret_cast<float*>(sum_b + dsto[u]);
+            if (dsto[u] != cur) {
+              if (cur >= 0) {
 #pragma unroll
-            for (int v = 0; v < V; ++v)
-              st_f4(dst + 4 * L * v, fma4_packed(wv[u], xv[u][v], ld_f4(dst + 4 * L * v)));
+                for (int v = 0; v < V; ++v) st_f4(reinterpret_cast<float*>(sum_b + cur) + 4 * L * v, acc[v]);
+              }
+              cur = dsto[u];
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc[v] = ld_f4(reinterpret_cast<const float*>(sum_b + cur) + 4 * L * v);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = fma4_packed(wv[u], xv[u][v], acc[v]);
           }
+        }
+        if (cur >= 0) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) st_f4(reinterpret_cast<float*>(sum_b + cur) + 4 * L * v, acc[v]);
         }
         __syncwarp();
 #pragma unroll
