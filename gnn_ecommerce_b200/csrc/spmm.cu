@@ -334,12 +334,13 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
     //     product is added to its slot. A row that began in an earlier run of the pass goes to the
     //     sub-warp's carry slot instead, added afterwards in sub-warp order (timing-independent).
     int n_flat;
-    unsigned okbits;
+    unsigned okbits, zbits;
     {
       int dgr = 0;
       if (lane < rows_here) dgr = s_rp[lane + 1] - s_rp[lane];
       const bool light = lane < rows_here && dgr <= light_max;
       okbits = __ballot_sync(0xffffffffu, light);
+      zbits = __ballot_sync(0xffffffffu, light && dgr == 0);   // rows without edges: their sum slot is never written
       const int dl = light ? dgr : 0;
       int incl = dl;
 #pragma unroll
@@ -352,9 +353,6 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
         s_P[lane] = incl - dl;
         s_D[lane] = (lane < rows_here ? s_rp[lane] : 0) - (incl - dl);   // CSR position = flat position + s_D[row]
       }
-#pragma unroll
-      for (int i = 0; i < (TF + NSUBW * LD) / 128; ++i)     // sums + carry slots (both multiples of 128 floats)
-        st_f4(s_sum + 128 * i + 4 * lane, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     {
       constexpr int U0 = V >= 3 ? 2 : 4;                   // gathers in flight per lane: U * V float4
@@ -393,6 +391,7 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
             for (int k = 1; k < NSUBW; ++k) q += (j >= k * len) ? 1 : 0;
             const bool carry = q > 0 && s_P[r] < base + q * len;   // the row began in an earlier run of this pass
             dst = (carry ? TF + q * LD : r * LD) * 4;
+            if (base > 0 && q == 0 && s_P[r] < base) dst |= 1;   // continued from the previous pass: keep its sum
             if (carry && j == q * len) s_carry_row[q] = r;
           }
           __syncwarp();                                    // in place: all reads of the batch before its writes
@@ -438,11 +437,13 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
             if (dsto[u] != cur) {
               if (cur >= 0) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) st_f4(reinterpret_cast<float*>(sum_b + cur) + 4 * L * v, acc[v]);
+                for (int v = 0; v < V; ++v) st_f4(reinterpret_cast<float*>(sum_b + (cur & ~1)) + 4 * L * v, acc[v]);
               }
               cur = dsto[u];
 #pragma unroll
-              for (int v = 0; v < V; ++v) acc[v] = ld_f4(reinterpret_cast<const float*>(sum_b + cur) + 4 * L * v);
+              for (int v = 0; v < V; ++v)                  // every slot has one writer per pass: start from zero
+                acc[v] = (cur & 1) ? ld_f4(reinterpret_cast<const float*>(sum_b + (cur & ~1)) + 4 * L * v)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v] = fma4_packed(wv[u], xv[u][v], acc[v]);
@@ -450,17 +451,15 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
         }
         if (cur >= 0) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) st_f4(reinterpret_cast<float*>(sum_b + cur) + 4 * L * v, acc[v]);
+          for (int v = 0; v < V; ++v) st_f4(reinterpret_cast<float*>(sum_b + (cur & ~1)) + 4 * L * v, acc[v]);
         }
         __syncwarp();
 #pragma unroll
-        for (int q = 1; q < NSUBW; ++q) {                  // carries, in sub-warp order; slots cleared for the next pass
+        for (int q = 1; q < NSUBW; ++q) {                  // carries, in sub-warp order
           const int cr = s_carry_row[q];
           if (cr >= 0)
-            for (int i = 4 * lane; i < LD; i += 128) {
+            for (int i = 4 * lane; i < LD; i += 128)
               st_f4(s_sum + cr * LD + i, add4(ld_f4(s_sum + cr * LD + i), ld_f4(s_carry + q * LD + i)));
-              st_f4(s_carry + q * LD + i, make_float4(0.f, 0.f, 0.f, 0.f));
-            }
         }
       }
     }
@@ -477,7 +476,7 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int off = t * LD + 4 * (sl + L * v);
-        const float4 s = ld_f4(s_sum + off);
+        const float4 s = ((zbits >> t) & 1u) ? make_float4(0.f, 0.f, 0.f, 0.f) : ld_f4(s_sum + off);
         if (MODE == EPI_PLAIN) {
           float4 r = make_float4(args.scale * s.x, args.scale * s.y, args.scale * s.z, args.scale * s.w);
           if (args.addend) {
