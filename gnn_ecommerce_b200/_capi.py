@@ -55,6 +55,7 @@ _SIGNATURES = {
     "lgc_profile_enable": (C.c_int, [C.c_int]),
     "lgc_profile_read": (C.c_int, [C.POINTER(c_f64), C.POINTER(C.c_longlong), C.c_int]),
     "lgc_graph_build": (C.c_int, [c_i64, c_i64, c_vp, c_vp, C.c_int, c_vp, C.POINTER(c_vp)]),
+    "lgc_graph_build_pairs": (C.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, C.c_int, c_vp, C.POINTER(c_vp)]),
     "lgc_graph_build_rect": (C.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
     "lgc_graph_destroy": (C.c_int, [c_vp]),
     "lgc_graph_get_info": (C.c_int, [c_vp, C.POINTER(GraphInfo)]),

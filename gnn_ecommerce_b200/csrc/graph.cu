@@ -42,15 +42,34 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   return x;
 }
 
+// Where the edge list comes from. CooEdges: the `[2, nnz]` int64 `edge_index` of df_to_graph.
+// PairEdges: the E interaction pairs themselves; edge e < E is a[e] -> b[e], edge E + e is
+// b[e] -> a[e] with the same weight -- the order in which df_to_graph concatenates the two
+// directions (src/utils_v2.py:155-158), so both sources give bit-identical graphs, without the
+// [2, 2E] int64 intermediate (6.4 GB at 200 M interactions).
+struct CooEdges {
+  const int64_t* ei; const float* ew; int64_t nnz;
+  __device__ __forceinline__ int64_t src(int64_t e) const { return ei[e]; }
+  __device__ __forceinline__ int64_t dst(int64_t e) const { return ei[nnz + e]; }
+  __device__ __forceinline__ float weight(int64_t e) const { return ew ? ew[e] : 1.0f; }
+};
+struct PairEdges {
+  const int64_t* a; const int64_t* b; const float* ew; int64_t n_pairs;
+  __device__ __forceinline__ int64_t src(int64_t e) const { return e < n_pairs ? a[e] : b[e - n_pairs]; }
+  __device__ __forceinline__ int64_t dst(int64_t e) const { return e < n_pairs ? b[e] : a[e - n_pairs]; }
+  __device__ __forceinline__ float weight(int64_t e) const { return ew ? ew[e < n_pairs ? e : e - n_pairs] : 1.0f; }
+};
+
 // keys = target id, vals = edge position; count in-degrees; range check; symmetry fingerprint
-__global__ void k_extract(const int64_t* __restrict__ ei, const float* __restrict__ ew, int64_t nnz,
+template <class Edges>
+__global__ void k_extract(Edges edges, int64_t nnz,
                           int64_t num_nodes, int64_t num_cols, int32_t* __restrict__ keys, int32_t* __restrict__ vals,
                           int32_t* __restrict__ counts, int* __restrict__ bad,
                           unsigned long long* __restrict__ fp) {
   unsigned long long h_fwd = 0, h_rev = 0;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz;
        e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = ei[e], c = ei[nnz + e];
+    int64_t r = edges.src(e), c = edges.dst(e);
     if (r < 0 || r >= num_cols || c < 0 || c >= num_nodes) {
       atomicExch(bad, 1);
       keys[e] = 0; vals[e] = (int32_t)e;
@@ -59,7 +78,7 @@ __global__ void k_extract(const int64_t* __restrict__ ei, const float* __restric
     keys[e] = (int32_t)c;
     vals[e] = (int32_t)e;
     atomicAdd(&counts[c], 1);
-    unsigned long long wb = ew ? (unsigned long long)__float_as_uint(ew[e]) : 0x3f800000ULL;
+    unsigned long long wb = (unsigned long long)__float_as_uint(edges.weight(e));
     h_fwd += mix64(((unsigned long long)r << 32 | (unsigned long long)c) ^ mix64(wb + 0x9e3779b97f4a7c15ULL));
     h_rev += mix64(((unsigned long long)c << 32 | (unsigned long long)r) ^ mix64(wb + 0x9e3779b97f4a7c15ULL));
   }
@@ -71,14 +90,15 @@ __global__ void k_extract(const int64_t* __restrict__ ei, const float* __restric
   if ((threadIdx.x & 31) == 0) { atomicAdd(&fp[0], h_fwd); atomicAdd(&fp[1], h_rev); }
 }
 
-__global__ void k_gather_csr(const int64_t* __restrict__ ei, const float* __restrict__ ew, int64_t nnz,
+template <class Edges>
+__global__ void k_gather_csr(Edges edges, int64_t nnz,
                              const int32_t* __restrict__ eid, int32_t* __restrict__ src,
                              float* __restrict__ w) {
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nnz;
        j += (int64_t)gridDim.x * blockDim.x) {
     int32_t e = eid[j];
-    src[j] = (int32_t)ei[e];
-    w[j] = ew ? ew[e] : 1.0f;
+    src[j] = (int32_t)edges.src(e);
+    w[j] = edges.weight(e);
   }
 }
 
@@ -238,21 +258,32 @@ extern "C" int lgc_graph_get_info(const lgc_graph_t* g, lgc_graph_info* info) {
   return LGC_OK;
 }
 
-static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, const int64_t* ei, const float* ew,
+template <class Edges>
+static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, Edges edges,
                             int normalize, void* stream_, lgc_graph_t** out);
 
 extern "C" int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* ei, const float* ew,
                                int normalize, void* stream_, lgc_graph_t** out) {
-  return graph_build_impl(num_nodes, num_nodes, nnz, ei, ew, normalize, stream_, out);
+  LGC_REQUIRE(nnz <= 0 || ei, "edge_index is null");
+  return graph_build_impl(num_nodes, num_nodes, nnz, CooEdges{ei, ew, nnz}, normalize, stream_, out);
 }
 
 extern "C" int lgc_graph_build_rect(int64_t num_rows, int64_t num_cols, int64_t nnz, const int64_t* ei,
                                     const float* ew, void* stream_, lgc_graph_t** out) {
-  return graph_build_impl(num_rows, num_cols, nnz, ei, ew, 0, stream_, out);
+  LGC_REQUIRE(nnz <= 0 || ei, "edge_index is null");
+  return graph_build_impl(num_rows, num_cols, nnz, CooEdges{ei, ew, nnz}, 0, stream_, out);
+}
+
+extern "C" int lgc_graph_build_pairs(int64_t num_nodes, int64_t n_pairs, const int64_t* a, const int64_t* b,
+                                     const float* ew, int normalize, void* stream_, lgc_graph_t** out) {
+  LGC_REQUIRE(n_pairs >= 0 && n_pairs < (1LL << 30), "n_pairs out of range");
+  LGC_REQUIRE(n_pairs == 0 || (a && b), "pair arrays are null");
+  return graph_build_impl(num_nodes, num_nodes, 2 * n_pairs, PairEdges{a, b, ew, n_pairs}, normalize, stream_, out);
 }
 
 // rows = targets (row 1 of edge_index) in [0, num_nodes); sources (row 0) in [0, num_cols)
-static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, const int64_t* ei, const float* ew,
+template <class Edges>
+static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, Edges edges,
                             int normalize, void* stream_, lgc_graph_t** out) {
   LGC_REQUIRE(out, "out_graph is null");
   *out = nullptr;
@@ -260,7 +291,6 @@ static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, co
   LGC_REQUIRE(num_cols > 0 && num_cols < (1LL << 31) - 64, "num_cols out of range");
   LGC_REQUIRE(!normalize || num_cols == num_nodes, "normalisation needs a square operator");
   LGC_REQUIRE(nnz >= 0 && nnz < (1LL << 31) - 64, "nnz out of range");
-  LGC_REQUIRE(nnz == 0 || ei, "edge_index is null");
   cudaStream_t stream = (cudaStream_t)stream_;
 
   DevBuf<int32_t> keys_in, keys_out, vals_in, counts, rowptr, src, eid, n_chunks, n_slots, n_split,
@@ -286,7 +316,7 @@ static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, co
 
   const int threads = 256;
   const int grid_e = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(nnz, threads), 1), kNumSMs * 16);
-  k_extract<<<grid_e, threads, 0, stream>>>(ei, ew, nnz, num_nodes, num_cols, keys_in.p, vals_in.p, counts.p,
+  k_extract<<<grid_e, threads, 0, stream>>>(edges, nnz, num_nodes, num_cols, keys_in.p, vals_in.p, counts.p,
                                             bad.p, fp.p);
   LGC_LAUNCH_CHECK();
 
@@ -302,7 +332,7 @@ static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, co
     LGC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, eid.p,
                                              (int)nnz, 0, end_bit, stream));
   LGC_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.p, rowptr.p, (int)n1, stream));
-  k_gather_csr<<<grid_e, threads, 0, stream>>>(ei, ew, nnz, eid.p, src.p, w.p);
+  k_gather_csr<<<grid_e, threads, 0, stream>>>(edges, nnz, eid.p, src.p, w.p);
   LGC_LAUNCH_CHECK();
 
   const int grid_rows_warp = (int)ceil_div(num_nodes * 32, threads);

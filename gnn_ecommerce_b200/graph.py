@@ -59,14 +59,61 @@ class Graph:
             rc = self._lib.lgc_graph_build(self.num_nodes, self.nnz, _ptr(ei), _ptr(ew),
                                            1 if normalize else 0, _stream(), C.byref(handle))
         _capi.check(rc, "lgc_graph_build")
+        self._adopt(handle)
+        self._edge_index, self._edge_weight = ei, ew          # kept for the transpose build
+
+    def _adopt(self, handle) -> None:
         self.handle = handle
         info = _capi.GraphInfo()
         _capi.check(self._lib.lgc_graph_get_info(self.handle, C.byref(info)), "lgc_graph_get_info")
         self.info = info
         self.is_symmetric = bool(info.is_symmetric)
-        self._edge_index, self._edge_weight = ei, ew          # kept for the transpose build
+        self._edge_index, self._edge_weight = None, None
         self._transpose: Optional["Graph"] = None
         self._ws = {}
+
+    @classmethod
+    def from_interactions(cls, user_idx: Tensor, item_idx: Tensor, weight: Optional[Tensor],
+                          num_nodes: int, normalize: bool = True) -> "Graph":
+        """The graph of `df_to_graph(train_df, True)` (reference `src/utils_v2.py:146-165`) built
+        from the frame's two id columns directly: `user_idx` and `item_idx` (already offset by
+        n_users, `src/utils_v2.py:128`) are int64 device tensors of E entries. Bit-identical to
+        `Graph(edge_index, edge_weight, ...)` on df_to_graph's output, without materialising the
+        `[2, 2E]` int64 COO. Pass the returned object wherever the module takes `edge_index`."""
+        if not user_idx.is_cuda:
+            raise RuntimeError("gnn_ecommerce_b200 runs on CUDA tensors only (no CPU fallback)")
+        if user_idx.dtype != torch.int64 or item_idx.dtype != torch.int64 or user_idx.shape != item_idx.shape \
+                or user_idx.dim() != 1:
+            raise ValueError("user_idx / item_idx must be int64 vectors of equal length")
+        a, b = user_idx.contiguous(), item_idx.to(user_idx.device).contiguous()
+        ew = None
+        if weight is not None:
+            if weight.numel() != a.numel():
+                raise ValueError("weight must have one entry per interaction")
+            ew = weight.to(device=a.device, dtype=torch.float32).contiguous()
+        self = cls.__new__(cls)
+        self._lib = _capi.lib()
+        self.device = a.device
+        self.num_nodes = int(num_nodes)
+        self.nnz = 2 * int(a.numel())
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self._lib.lgc_graph_build_pairs(self.num_nodes, int(a.numel()), _ptr(a), _ptr(b), _ptr(ew),
+                                                 1 if normalize else 0, _stream(), C.byref(handle))
+        _capi.check(rc, "lgc_graph_build_pairs")
+        self._adopt(handle)
+        return self
+
+    # ---- enough of the tensor surface for a Graph to stand in for `edge_index` in the module API
+    is_cuda = True
+    _version = 0
+
+    def data_ptr(self) -> int:
+        return int(self.handle.value or 0)
+
+    @property
+    def shape(self):
+        return (2, self.nnz)
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -101,6 +148,8 @@ class Graph:
         if self.is_symmetric:
             return self
         if self._transpose is None:
+            if self._edge_index is None:
+                raise RuntimeError("a graph built from interaction pairs is symmetric by construction")
             self._transpose = Graph(self._edge_index.flip(0), self.w_hat_edge_order(),
                                     self.num_nodes, normalize=False)
         return self._transpose
@@ -137,8 +186,12 @@ _CACHE: "OrderedDict[Tuple, Graph]" = OrderedDict()
 _CACHE_SIZE = 4
 
 
-def graph_for(edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int,
+def graph_for(edge_index, edge_weight: Optional[Tensor], num_nodes: int,
               normalize: bool = True) -> Graph:
+    if isinstance(edge_index, Graph):                      # a prebuilt graph passed where edge_index goes
+        if edge_index.num_nodes != int(num_nodes):
+            raise ValueError("the graph was built for a different number of nodes")
+        return edge_index
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version,
            None if edge_weight is None else (edge_weight.data_ptr(), edge_weight._version,
                                              edge_weight.dtype),

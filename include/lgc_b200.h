@@ -77,6 +77,15 @@ int lgc_graph_build(int64_t num_nodes, int64_t nnz, const int64_t* d_edge_index,
                     lgc_graph_t** out_graph);
 int lgc_graph_destroy(lgc_graph_t* graph);
 
+/* Same graph straight from the E interaction pairs (the frame's `user_id_idx` / offset `item_id_idx`
+ * columns, reference src/utils_v2.py:128,146-165): edge e is a[e] -> b[e], edge E + e is
+ * b[e] -> a[e] with the same weight, i.e. the order in which df_to_graph concatenates the two
+ * directions, so the result is bit-identical to lgc_graph_build on df_to_graph's output -- without
+ * the [2, 2E] int64 COO intermediate. d_a / d_b: device int64 [n_pairs]. */
+int lgc_graph_build_pairs(int64_t num_nodes, int64_t n_pairs, const int64_t* d_a, const int64_t* d_b,
+                          const float* d_edge_weight, int normalize, void* stream,
+                          lgc_graph_t** out_graph);
+
 /* Rectangular operator for the row-partitioned multi-GPU path: rows = targets in [0, num_rows)
  * (a GPU's shard of destination nodes, ids shifted to the shard), sources in [0, num_cols) (ids
  * into the all-gathered table). Weights are used as given -- pass the w_hat of the global graph

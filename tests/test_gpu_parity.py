@@ -399,3 +399,27 @@ def test_checkpoint_roundtrip_in_the_reference_format(tmp_path):
         assert torch.allclose(a, c, rtol=1e-5, atol=1e-9), (a, c)
     dw = (model.embedding.weight.detach() - model2.embedding.weight.detach()).abs().max().item()
     assert dw < 1e-6, dw
+
+
+# --------------------------------------------------------------------------- graph ingest from pairs
+def test_graph_from_interaction_pairs_is_bit_identical_to_df_to_graph():
+    """`Graph.from_interactions` (lgc_graph_build_pairs) == `Graph` on df_to_graph's COO
+    (reference src/utils_v2.py:146-165): same CSR, same normalised weights, and the module accepts the
+    prebuilt graph where it takes edge_index."""
+    from gnn_ecommerce_b200.graph import Graph
+    g = synth.make_graph(3000, 200, 20_000, seed=23)
+    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
+    ref = Graph(ei.to(DEV), ew.to(DEV), g.num_nodes)
+    got = Graph.from_interactions(torch.from_numpy(g.user).to(DEV), torch.from_numpy(g.item).to(DEV),
+                                  torch.from_numpy(g.weight).to(DEV), g.num_nodes)
+    assert got.nnz == ref.nnz and got.is_symmetric
+    a, b = ref.arrays(), got.arrays()
+    for k in ("rowptr", "src", "eid", "w_hat", "deg", "dis"):
+        assert torch.equal(a[k], b[k]), k
+    torch.manual_seed(3)
+    init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, 64)).numpy()
+    model = _model(g.num_nodes, 64, 3, init)
+    with torch.no_grad():
+        e_ref = model.get_embedding(ei.to(DEV), ew.to(DEV))
+        e_got = model.get_embedding(got, None)
+    assert torch.equal(e_ref, e_got)
