@@ -423,3 +423,4 @@ def test_graph_from_interaction_pairs_is_bit_identical_to_df_to_graph():
         e_ref = model.get_embedding(ei.to(DEV), ew.to(DEV))
         e_got = model.get_embedding(got, None)
     assert torch.equal(e_ref, e_got)
+
