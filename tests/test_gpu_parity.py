@@ -424,3 +424,21 @@ def test_graph_from_interaction_pairs_is_bit_identical_to_df_to_graph():
         e_got = model.get_embedding(got, None)
     assert torch.equal(e_ref, e_got)
 
+
+
+def test_resume_from_a_checkpoint_written_by_the_reference():
+    """tests/golden/ref_checkpoint_tiny.pt was written by the reference's own `save_model` after two
+    reference steps (make_ref_checkpoint.py); `load_model` restores weights, Adam moments and the step
+    count, and the next fused step lands where the reference's third step landed."""
+    import os
+    from gnn_ecommerce_b200 import load_model
+    here = os.path.dirname(os.path.abspath(__file__))
+    z = np.load(os.path.join(here, "golden", "tiny.npz"))
+    nxt = np.load(os.path.join(here, "golden", "ref_checkpoint_tiny_next.npz"))
+    model, trainer, ck = load_model(os.path.join(here, "golden", "ref_checkpoint_tiny.pt"), DEV)
+    assert trainer.step_count == 2 and trainer.lr == ck["hyperparams"]["lr"]
+    ei, ew = torch.from_numpy(z["edge_index"]).to(DEV), torch.from_numpy(z["edge_weight"]).to(DEV)
+    u, p, n = (torch.from_numpy(np.ascontiguousarray(x)).to(DEV) for x in nxt["triple"])
+    loss3 = trainer.step(ei, ew, u, p, n, DECAY).cpu().numpy()
+    assert np.allclose(loss3, nxt["losses"], rtol=1e-5, atol=0), (loss3, nxt["losses"])
+    assert rel(model.embedding.weight.detach().cpu().numpy(), nxt["w3"]) < 1e-5
