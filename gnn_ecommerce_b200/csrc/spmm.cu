@@ -120,9 +120,8 @@ __device__ __forceinline__ void epilogue(const EpiArgs& a, size_t off, float4 s)
 // epilogue runs in shared memory in place, and lane 0 sends the result tiles back with bulk-async
 // stores. Measured (profiles/r1f_light_bottleneck.md): the kernel is bound by issued instructions,
 // not by the gather loads -- removing every gather load changes its time by 3 %.
-// Rows above `light_max` keep their shared-memory slots untouched (read-modify-write operands are
-// stored back unchanged, plain outputs are overwritten by the heavy-row kernels that run after this
-// one on the same stream).
+// Rows above `light_max` (hub rows) belong to the heavy-row kernels: this kernel neither sums nor
+// writes them (a tile that contains hub rows leaves as one bulk store per run of light rows).
 constexpr int kLightWarpsMax = 5;      // warps per CTA (each fully independent): see LightCfg::WARPS
 constexpr size_t kMaxDynamicSmem = 227 * 1024;   // per CTA on sm_100
 constexpr int kLightStageCap = 128;    // CSR entries of a tile staged per warp and stage
@@ -142,8 +141,9 @@ struct LightCfg {
   static constexpr size_t stage_bytes(int nbuf) {
     return (size_t)nbuf * TILE_FLOATS * 4 + RP_INTS * 4 + 2 * CSR_INTS * 4;
   }
-  // after the ring: 6 mbarriers | row sums S [TR x LD] | carry rows C [NSUBW x LD] | row of flat edge | s_P, s_D | carry row ids | phase clocks
-  static constexpr size_t ROWID_BYTES = (size_t)kLightStageCap * 2;  // uint16 per flat edge of a pass
+  // after the ring: 6 mbarriers | row sums S [TR x LD] | carry rows C [NSUBW x LD] | sum slot of every flat
+  // edge (uint16) | s_P, s_D | carry row ids | phase clocks
+  static constexpr size_t ROWID_BYTES = (size_t)kLightStageCap * 2;  // uint16 per flat edge (or padding slot) of a pass
   static constexpr size_t SCRATCH_BYTES =
       (size_t)TILE_FLOATS * 4 + (size_t)NSUBW * LD * 4 + ROWID_BYTES + 2 * 33 * 4 + 8 + 32 + 64;
   static constexpr size_t warp_bytes(int nbuf) { return 2 * stage_bytes(nbuf) + 64 + SCRATCH_BYTES; }
@@ -327,12 +327,14 @@ k_spmm_light(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src
     // ---- gathers, EDGE-balanced. One sub-warp per row made the warp wait for the longest of the
     // tile's rows (power law) with most lanes idle, and the kernel is bound by issued instructions.
     // Instead the tile's light edges form one flat list (exclusive prefix s_P over the rows; rows
-    // above light_max contribute nothing), handled in passes of <= kLightStageCap edges:
+    // above light_max contribute nothing), handled in passes of <= CAP edges:
     //  1. compaction, one LANE per edge: row by bisection, then (source row offset, weight,
     //     shared-memory slot of the sum) are written over the staged CSR slice in flat order;
-    //  2. the pass is cut into NSUBW equal runs, one per sub-warp, U gathers in flight each; every
-    //     product is added to its slot. A row that began in an earlier run of the pass goes to the
-    //     sub-warp's carry slot instead, added afterwards in sub-warp order (timing-independent).
+    //  2. the pass is cut into NSUBW equal runs (padded to a multiple of U with weight-0 slots), one
+    //     per sub-warp, U gathers in flight each; the sum of the current slot stays in registers and
+    //     is stored when the run leaves the slot. Every slot has ONE writer per pass: a row that began
+    //     in an earlier run of the pass goes to the sub-warp's carry slot instead, added afterwards in
+    //     sub-warp order (timing-independent), so slots start from zero and need no clearing.
     int n_flat;
     unsigned okbits, zbits;
     {
