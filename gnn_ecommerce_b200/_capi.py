@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "liblgc_b200.so")
+# LGC_B200_LIB: another build of the same library (A/B experiments under profiles/experiments)
+LIB_PATH = os.environ.get("LGC_B200_LIB") or os.path.join(_PKG, "liblgc_b200.so")
 
 c_i64, c_i32, c_f32, c_f64, c_vp, c_sz = C.c_int64, C.c_int32, C.c_float, C.c_double, C.c_void_p, C.c_size_t
 

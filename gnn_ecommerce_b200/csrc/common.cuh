@@ -132,6 +132,13 @@ static inline bool row_shape(int ld, RowShape* rs) {
 
 }  // namespace lgc
 
+// Sweep schedule of the high-degree rows (sweep.cu): built lazily per accumulator-slot count.
+namespace lgc {
+struct SweepSched;
+void sweep_destroy(SweepSched* s);
+}
+constexpr int kMaxSweepScheds = 4;
+
 // Opaque graph handle (definition shared by the .cu files).
 struct lgc_graph {
   int64_t num_nodes = 0, nnz = 0;
@@ -153,4 +160,9 @@ struct lgc_graph {
   int4* chunks = nullptr;       // {row, beg, end, partial_slot or -1}, ordered by first source
   int4* split_rows = nullptr;   // {row, first_slot, n_slots, 0}
   int64_t num_partial_slots = 0;   // one [ld] partial row per chunk of a split row (workspace)
+  int64_t num_cols = 0;            // rows of the gathered table (== num_nodes unless rectangular)
+  // lazily built sweep schedules (mutable cache: the handle is logically const for its users)
+  mutable lgc::SweepSched* sweep[kMaxSweepScheds] = {};
+  mutable int sweep_failed[kMaxSweepScheds] = {};   // slot counts for which no schedule exists
+  mutable int n_sweep_failed = 0;
 };

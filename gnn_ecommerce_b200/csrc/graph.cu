@@ -240,6 +240,7 @@ extern "C" int lgc_graph_destroy(lgc_graph_t* g) {
   cudaFree(g->rowptr); cudaFree(g->src); cudaFree(g->eid); cudaFree(g->w_hat);
   cudaFree(g->deg); cudaFree(g->dis); cudaFree(g->chunks); cudaFree(g->split_rows);
   cudaFree(g->hsrc); cudaFree(g->hw);
+  for (int i = 0; i < kMaxSweepScheds; ++i) lgc::sweep_destroy(g->sweep[i]);
   delete g;
   return LGC_OK;
 }
@@ -416,7 +417,7 @@ static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, Ed
   LGC_CUDA(cudaStreamSynchronize(stream));
 
   lgc_graph* g = new lgc_graph();
-  g->num_nodes = num_nodes; g->nnz = nnz;
+  g->num_nodes = num_nodes; g->nnz = nnz; g->num_cols = num_cols;
   g->is_symmetric = (num_cols == num_nodes && h_fp[0] == h_fp[1]) ? 1 : 0;
   g->light_max_degree = kLightMaxDegree;
   g->num_chunks = h_tot[0];

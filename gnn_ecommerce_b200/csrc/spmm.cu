@@ -829,15 +829,31 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   // light CTAs per SM that leave room for the overlapping heavy CTAs
   const size_t heavy_need = kHeavyCtasOverlap * (HC::SMEM + kSmemPerCtaReserved);
   const int light_cap = heavy_need < kSmemPerSM ? (int)((kSmemPerSM - heavy_need) / (smem + kSmemPerCtaReserved)) : 0;
-  OverlapCtx* ov = (MODE != EPI_ADAM && g->num_chunks > 0 && light_cap >= 1) ? overlap_ctx() : nullptr;
+  OverlapCtx* ov = (MODE != EPI_ADAM && g->num_chunks > 0 && light_cap >= 1 && !sweep_get(g, HC::LD)) ? overlap_ctx() : nullptr;
   cudaStream_t hs = st;
   if (ov) {
     LGC_CUDA(cudaEventRecord(ov->fork, st));
     LGC_CUDA(cudaStreamWaitEvent(ov->side, ov->fork, 0));
     hs = ov->side;
   }
-  // ---- heavy rows (+ the sums of split rows): launched first so that their CTAs find room
-  if (g->num_chunks > 0) {
+  // ---- high-degree rows: the sweep kernel (sweep.cu) when a schedule exists for this row width ...
+  const SweepSched* sw = g->num_chunks > 0 ? sweep_get(g, HC::LD) : nullptr;
+  if (sw) {
+    int rc = launch_sweep(g, sw, HC::LD, x, (EpiMode)MODE, a, partials, st);
+    if (rc) return rc;
+    int64_t n_split = 0;
+    const int4* split = sweep_split_rows(sw, &n_split);
+    if (n_split > 0) {
+      {
+        ProfScope ps(PROF_FINISH + (MODE & 3), st);
+        k_spmm_finish<L, V, MODE><<<(int)n_split, threads, 0, st>>>(split, (int)n_split, partials, a);
+      }
+      LGC_LAUNCH_CHECK();
+    }
+  }
+  // ---- ... else the chunked heavy-row kernel (+ the sums of split rows): launched first so that
+  // their CTAs find room
+  if (!sw && g->num_chunks > 0) {
     static int occ_heavy = 0;            // per instantiation: resident CTAs per SM
     if (!occ_heavy) {
       LGC_CUDA(cudaFuncSetAttribute(k_spmm_heavy<L, V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -916,7 +932,9 @@ __global__ void k_scale(const float4* __restrict__ x, float4* __restrict__ y, fl
 }  // namespace
 
 size_t spmm_partials_floats(const lgc_graph* g, int ld) {
-  return (size_t)g->num_partial_slots * (size_t)ld;
+  const SweepSched* sw = g->num_chunks > 0 ? sweep_get(g, ld) : nullptr;   // builds the schedule on first use
+  const size_t slots = sw ? sweep_partial_slots(sw) : (size_t)g->num_partial_slots;
+  return slots * (size_t)ld;
 }
 
 int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const EpiArgs& a,

@@ -85,6 +85,16 @@ size_t spmm_partials_floats(const lgc_graph* g, int ld);
 int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const EpiArgs& args,
                 float* partials, cudaStream_t stream);
 
+// ---- sweep path of the high-degree rows (sweep.cu). `sweep_get` builds the schedule for this row
+// width on first use (synchronous, allocates inside the handle; never during stream capture: the
+// workspace-size queries call it first) and returns nullptr when the rows stay with the chunked
+// heavy-row kernel (unsupported width, node ids too large for the packed records, LGC_SWEEP=0).
+const SweepSched* sweep_get(const lgc_graph* g, int ld);
+size_t sweep_partial_slots(const SweepSched* s);
+const int4* sweep_split_rows(const SweepSched* s, int64_t* n);
+int launch_sweep(const lgc_graph* g, const SweepSched* s, int ld, const float* x, EpiMode mode,
+                 const EpiArgs& args, float* partials, cudaStream_t st);
+
 // out = sum_l alpha_l A^l x0 with K-1 scratch tables `xs` (see spmm.cu)
 int propagate_chain(const lgc_graph* g, int ld, int K, const float* alpha, const float* x0, float* out,
                     float* const* xs, float* partials, cudaStream_t st);
