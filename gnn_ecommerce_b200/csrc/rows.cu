@@ -1,0 +1,175 @@
+// Rows kernel: Y[r] = sum_e w_e X[src_e] with the fused epilogue for the rows the sweep does not take
+// -- at the Cosmetics-Shop shape the 1.6 M user rows (mean in-degree ~3), whose sources are the
+// 54 K item rows (L2 / L1 resident). LGConv's `propagate` for those rows (reference call site
+// src/lightgcn.py:96) plus the ATen passes the epilogue replaces (src/lightgcn.py:93,97;
+// src/train_lightgcn.py:147).
+//
+// Round 1 staged whole row tiles in shared memory with bulk-async copies and balanced the tile's
+// edges over the lanes; it was bound by issued instructions (833 warp-instructions per 8-row tile,
+// 56 % of the HBM roofline) and its 227 KB of shared memory left no L1 for the gathered item rows.
+// This kernel does as little as possible per row instead:
+//   * one sub-warp of L lanes per row, V float4 per lane; the row streams (epilogue operands in,
+//     results out) are plain coalesced 128-bit loads / stores with streaming cache hints, issued
+//     before the gathers so that their HBM latency overlaps the gather latency;
+//   * a row's edges are ONE 8-byte (source, weight) record per lane (rows up to L edges: one load),
+//     broadcast inside the sub-warp with shuffles; the gathers of a row are issued back to back;
+//   * rows are taken in blocks of 256 consecutive rows (all row-stream traffic of a CTA stays inside
+//     a 64 KB window per table) but INSIDE a block in descending-degree order (graph build), so the
+//     4 sub-warps of a warp work on rows of equal length: no power-law divergence, no edge balancing;
+//   * no shared-memory tiles: the unified L1 keeps the hot item rows (a few hundred items carry half
+//     of the edges), which takes that traffic off the L2 -> SM path.
+// Edges of a row are added in CSR (= edge-list) order, like the CPU scatter_add_ of the reference.
+#include "epilogue.cuh"
+
+namespace lgc {
+namespace {
+
+constexpr int kRowsThreads = 256;
+
+template <int L, int V, int MODE>
+__global__ void __launch_bounds__(kRowsThreads)
+k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, const uint8_t* __restrict__ perm,
+            const int32_t* __restrict__ blk_cnt, int n_blocks, int num_rows, const float* __restrict__ x,
+            EpiArgs args) {
+  constexpr int LD = 4 * L * V, NSUB = 32 / L, SUBS = (kRowsThreads / 32) * NSUB, G = L < 4 ? L : 4;
+  static_assert(kRowsThreads == kRowsBlock, "one thread loads one row's metadata");
+  __shared__ int s_rp[2][kRowsBlock + 1];
+  __shared__ uint8_t s_perm[2][kRowsBlock];
+  const int tid = threadIdx.x, lane = tid & 31, wic = tid >> 5, sw = lane / L, sl = lane % L;
+  const int sub = wic * NSUB + sw;
+  const float* const xl = x + 4 * sl;
+  int buf = 0;
+  for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, buf ^= 1) {
+    const int row0 = b * kRowsBlock;
+    const int cnt = blk_cnt[b];
+    s_rp[buf][tid] = rowptr[min(row0 + tid, num_rows)];
+    if (tid == 0) s_rp[buf][kRowsBlock] = rowptr[min(row0 + kRowsBlock, num_rows)];
+    s_perm[buf][tid] = perm[row0 + tid];
+    __syncthreads();                                   // two buffers: one barrier per block is enough
+    for (int j0 = 0; j0 < cnt; j0 += SUBS) {
+      const int j = j0 + sub;
+      const bool valid = j < cnt;
+      int e0 = 0, deg = 0, r = row0;
+      if (valid) {
+        const int lr = s_perm[buf][j];
+        r = row0 + lr;
+        e0 = s_rp[buf][lr];
+        deg = s_rp[buf][lr + 1] - e0;
+      }
+      const int dmax = __reduce_max_sync(0xffffffffu, deg);
+      int2 my = make_int2(0, 0);                       // first L records of the row, one per lane
+      if (sl < deg) my = __ldg(rec + e0 + sl);
+      const size_t off = (size_t)r * LD + 4 * sl;
+      EpiPre<MODE, 4> pre[V];
+      if (MODE != EPI_FWD_FINAL && valid) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) epi_preload_w<MODE, 4>(args, off + 4 * L * v, pre[v]);
+      }
+      float acc[V][4];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[v][i] = 0.f;
+      for (int base = 0; base < dmax; base += L) {
+        if (base > 0) {
+          my = make_int2(0, 0);
+          if (base + sl < deg) my = __ldg(rec + e0 + base + sl);
+        }
+        const int n = deg - base;                      // edges left in this row (<= 0: none)
+#pragma unroll
+        for (int t0 = 0; t0 < L; t0 += G) {
+          if (base + t0 >= dmax) break;                // warp-uniform
+          float xv[G][V][4], wv[G];
+#pragma unroll
+          for (int t = 0; t < G; ++t) {
+            const int s = __shfl_sync(0xffffffffu, my.x, t0 + t, L);
+            wv[t] = __int_as_float(__shfl_sync(0xffffffffu, my.y, t0 + t, L));
+            if (t0 + t < n) {
+              const float* xr = xl + (size_t)(unsigned)s * LD;
+#pragma unroll
+              for (int v = 0; v < V; ++v) ldv_nc<4>(xr + 4 * L * v, xv[t][v]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xv[t][v][i] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < G; ++t)                  // edge order kept per row
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[v][i] = fmaf(wv[t], xv[t][v][i], acc[v][i]);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (MODE == EPI_FWD_FINAL) epilogue_w<MODE, 4>(args, off + 4 * L * v, acc[v]);
+          else epi_finish_w<MODE, 4>(args, off + 4 * L * v, acc[v], pre[v]);
+        }
+      }
+    }
+  }
+}
+
+template <int L, int V, int MODE>
+int launch_rows_lvm(const RowPlan* p, const float* x, const EpiArgs& a, const int32_t* rowptr, cudaStream_t st) {
+  static int occ_dev[64] = {};
+  int dev = 0;
+  LGC_CUDA(cudaGetDevice(&dev));
+  int occ = (dev >= 0 && dev < 64) ? occ_dev[dev] : 0;
+  static int sms_dev[64] = {};
+  if (!occ) {
+    LGC_CUDA(cudaFuncSetAttribute(k_spmm_rows<L, V, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));   // ~36 KB of shared memory, the rest L1
+    LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_rows<L, V, MODE>, kRowsThreads, 0));
+    if (occ < 1) occ = 1;
+    int sms = 0;
+    LGC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) { occ_dev[dev] = occ; sms_dev[dev] = sms; }
+    else sms_dev[0] = sms;
+  }
+  const int sms = (dev >= 0 && dev < 64) ? sms_dev[dev] : sms_dev[0];
+  const int grid = (int)std::min<int64_t>((int64_t)sms * occ, p->n_blocks);
+  if (grid <= 0) return LGC_OK;
+  ProfScope ps(PROF_LIGHT + (MODE & 3), st);
+  k_spmm_rows<L, V, MODE><<<grid, kRowsThreads, 0, st>>>(rowptr, p->rec, p->perm, p->blk_cnt, (int)p->n_blocks,
+                                                         (int)p->num_rows, x, a);
+  return LGC_OK;
+}
+
+template <int L, int V>
+int launch_rows_lv(const RowPlan* p, const float* x, EpiMode mode, const EpiArgs& a, const int32_t* rowptr,
+                   cudaStream_t st) {
+  switch (mode) {
+    case EPI_PLAIN: return launch_rows_lvm<L, V, EPI_PLAIN>(p, x, a, rowptr, st);
+    case EPI_FWD_INIT: return launch_rows_lvm<L, V, EPI_FWD_INIT>(p, x, a, rowptr, st);
+    case EPI_FWD_RMW: return launch_rows_lvm<L, V, EPI_FWD_RMW>(p, x, a, rowptr, st);
+    case EPI_ADAM: return launch_rows_lvm<L, V, EPI_ADAM>(p, x, a, rowptr, st);
+    case EPI_FWD_FINAL: return launch_rows_lvm<L, V, EPI_FWD_FINAL>(p, x, a, rowptr, st);
+  }
+  return LGC_ERR_INVALID;
+}
+
+}  // namespace
+
+int launch_rows(const lgc_graph* g, const RowPlan* plan, int ld, const float* x, EpiMode mode, const EpiArgs& a,
+                cudaStream_t st) {
+  if (!g || !plan) return LGC_ERR_INVALID;
+  int rc = LGC_ERR_UNSUPPORTED;
+  // sub-warp geometry per row width: L lanes x V float4 (few lanes per row: more rows per warp instruction)
+#define LGC_ROWS_CASE(LDV, LL, LV) case LDV: rc = launch_rows_lv<LL, LV>(plan, x, mode, a, g->rowptr, st); break;
+  switch (ld) {
+    LGC_ROWS_CASE(64, 8, 2) LGC_ROWS_CASE(128, 16, 2) LGC_ROWS_CASE(192, 16, 3) LGC_ROWS_CASE(256, 16, 4)
+    LGC_ROWS_CASE(32, 8, 1) LGC_ROWS_CASE(96, 8, 3) LGC_ROWS_CASE(160, 8, 5)
+    LGC_ROWS_CASE(16, 4, 1) LGC_ROWS_CASE(48, 4, 3) LGC_ROWS_CASE(80, 4, 5)
+    default: break;
+  }
+#undef LGC_ROWS_CASE
+  if (rc) return rc;
+  LGC_LAUNCH_CHECK();
+  return LGC_OK;
+}
+
+}  // namespace lgc

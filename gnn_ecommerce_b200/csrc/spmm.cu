@@ -829,7 +829,7 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   // light CTAs per SM that leave room for the overlapping heavy CTAs
   const size_t heavy_need = kHeavyCtasOverlap * (HC::SMEM + kSmemPerCtaReserved);
   const int light_cap = heavy_need < kSmemPerSM ? (int)((kSmemPerSM - heavy_need) / (smem + kSmemPerCtaReserved)) : 0;
-  OverlapCtx* ov = (MODE != EPI_ADAM && g->num_chunks > 0 && light_cap >= 1 && !sweep_get(g, HC::LD)) ? overlap_ctx() : nullptr;
+  OverlapCtx* ov = (MODE != EPI_ADAM && g->num_chunks > 0 && light_cap >= 1 && !rows_kernel_enabled() && !sweep_get(g, HC::LD)) ? overlap_ctx() : nullptr;
   cudaStream_t hs = st;
   if (ov) {
     LGC_CUDA(cudaEventRecord(ov->fork, st));
@@ -837,8 +837,8 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
     hs = ov->side;
   }
   // ---- high-degree rows: the sweep kernel (sweep.cu) when a schedule exists for this row width ...
-  const SweepSched* sw = g->num_chunks > 0 ? sweep_get(g, HC::LD) : nullptr;
-  if (sw) {
+  const SweepSched* sw = (g->num_chunks > 0 || rows_kernel_enabled()) ? sweep_get(g, HC::LD) : nullptr;
+  if (sw && sweep_has_rows(sw)) {
     int rc = launch_sweep(g, sw, HC::LD, x, (EpiMode)MODE, a, partials, st);
     if (rc) return rc;
     int64_t n_split = 0;
@@ -882,7 +882,9 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
     }
   }
   if (ov) LGC_CUDA(cudaEventRecord(ov->join, hs));
-  // ---- light rows
+  // ---- all other rows: the rows kernel (rows.cu) over the schedule's row plan ...
+  if (sw && sweep_row_plan(sw)) return launch_rows(g, sweep_row_plan(sw), HC::LD, x, (EpiMode)MODE, a, st);
+  // ---- ... or the round-1 light-row kernel (rows up to light_max_degree)
   {
     static int occ_light[kMaxHist + 1] = {};   // per instantiation and buffer count: resident CTAs per SM
     static size_t smem_set = 0;
@@ -932,7 +934,7 @@ __global__ void k_scale(const float4* __restrict__ x, float4* __restrict__ y, fl
 }  // namespace
 
 size_t spmm_partials_floats(const lgc_graph* g, int ld) {
-  const SweepSched* sw = g->num_chunks > 0 ? sweep_get(g, ld) : nullptr;   // builds the schedule on first use
+  const SweepSched* sw = (g->num_chunks > 0 || rows_kernel_enabled()) ? sweep_get(g, ld) : nullptr;   // builds the schedule on first use
   const size_t slots = sw ? sweep_partial_slots(sw) : (size_t)g->num_partial_slots;
   return slots * (size_t)ld;
 }

@@ -90,6 +90,22 @@ int launch_spmm(const lgc_graph* g, int ld, const float* x, EpiMode mode, const 
 // workspace-size queries call it first) and returns nullptr when the rows stay with the chunked
 // heavy-row kernel (unsupported width, node ids too large for the packed records, LGC_SWEEP=0).
 const SweepSched* sweep_get(const lgc_graph* g, int ld);
+bool sweep_has_rows(const SweepSched* s);          // false: no row qualified, nothing to launch
+// The rows the sweep does not take, for the rows kernel (rows.cu): blocks of kRowsBlock consecutive
+// rows; perm[b * kRowsBlock + j] = local index of the j-th of the block's blk_cnt[b] rows in
+// descending-degree order; rec = (source, weight bits) per CSR entry. LGC_ROWS=0 keeps the round-1
+// light-row kernel instead (no plan).
+constexpr int kRowsBlock = 256;
+struct RowPlan {
+  int64_t n_blocks = 0, num_rows = 0;
+  uint8_t* perm = nullptr;
+  int32_t* blk_cnt = nullptr;
+  int2* rec = nullptr;
+};
+const RowPlan* sweep_row_plan(const SweepSched* s);
+bool rows_kernel_enabled();
+int launch_rows(const lgc_graph* g, const RowPlan* plan, int ld, const float* x, EpiMode mode, const EpiArgs& args,
+                cudaStream_t st);
 size_t sweep_partial_slots(const SweepSched* s);
 const int4* sweep_split_rows(const SweepSched* s, int64_t* n);
 int launch_sweep(const lgc_graph* g, const SweepSched* s, int ld, const float* x, EpiMode mode,

@@ -62,14 +62,23 @@ struct SweepSched {
   int2* rec = nullptr;           // [n_iters * 32] {source | slot << src_bits, weight bits}
   int2* unit_rows = nullptr;     // [n_units * S] {row, partial slot or -1}; row < 0: unused
   int4* split_rows = nullptr;    // [n_split_rows] {row, first partial slot, pieces, 0}
+  // row plan of the remaining ("light") rows for rows.cu -- only when the rows kernel is enabled
+  RowPlan plan;
 };
 
 void sweep_destroy(SweepSched* s) {
   if (!s) return;
   cudaFree(s->warp_ptr); cudaFree(s->rec); cudaFree(s->unit_rows); cudaFree(s->split_rows);
+  cudaFree(s->plan.perm); cudaFree(s->plan.blk_cnt); cudaFree(s->plan.rec);
   delete s;
 }
 size_t sweep_partial_slots(const SweepSched* s) { return s ? (size_t)s->n_partial_slots : 0; }
+const RowPlan* sweep_row_plan(const SweepSched* s) { return (s && s->plan.perm) ? &s->plan : nullptr; }
+bool sweep_has_rows(const SweepSched* s) { return s && s->n_iters > 0; }
+bool rows_kernel_enabled() {
+  static const bool on = [] { const char* e = getenv("LGC_ROWS"); return !(e && atoi(e) == 0); }();
+  return on;
+}
 const int4* sweep_split_rows(const SweepSched* s, int64_t* n) {
   *n = s ? s->n_split_rows : 0;
   return s ? s->split_rows : nullptr;
@@ -135,6 +144,13 @@ __global__ void k_sweep_fill(int64_t n_records, int n_warps, const int32_t* __re
   rec[t] = r;
 }
 
+// (source, weight) of every CSR entry side by side: the rows kernel reads a row's edges as one
+// 8-byte record per lane
+__global__ void k_interleave(int64_t nnz, const int32_t* __restrict__ src, const float* __restrict__ w, int2* __restrict__ rec) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x)
+    rec[j] = make_int2(src[j], __float_as_int(w[j]));
+}
+
 template <typename T>
 struct Dev {
   T* p = nullptr;
@@ -170,21 +186,29 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   SWEEP_CUDA(cudaDeviceSynchronize());
   SWEEP_CUDA(cudaMemcpy(rp.data(), g->rowptr, ((size_t)n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
 
-  // ---- sweep rows: everything above the light-row threshold, by degree
+  // ---- sweep rows: by degree, everything above the threshold up to the accumulator capacity. With
+  // the rows kernel (rows.cu) the rest may have any degree; with the round-1 light-row kernel
+  // (LGC_ROWS=0) every row above its limit must fit.
+  const bool with_plan = rows_kernel_enabled();
+  static const int rows_max_degree = [] { const char* e = getenv("LGC_ROWS_MAX_DEGREE"); int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+  const int threshold = with_plan ? rows_max_degree : g->light_max_degree;
   std::vector<int32_t> rows;
-  int64_t n_edges = 0;
-  for (int64_t r = 0; r < n; ++r) {
-    const int d = rp[r + 1] - rp[r];
-    if (d > g->light_max_degree) { rows.push_back((int32_t)r); n_edges += d; }
-  }
-  if (rows.empty()) return nullptr;
-  if ((int64_t)rows.size() > (int64_t)n_units * S) return nullptr;   // more rows than accumulator slots
+  for (int64_t r = 0; r < n; ++r)
+    if (rp[r + 1] - rp[r] > threshold) rows.push_back((int32_t)r);
   std::stable_sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) {
     return rp[a + 1] - rp[a] > rp[b + 1] - rp[b];
   });
+  const int64_t capacity = (int64_t)n_units * S * 9 / 10;        // leave slots for the pieces of split rows
+  if ((int64_t)rows.size() > capacity) {
+    if (!with_plan) return nullptr;
+    rows.resize((size_t)capacity);
+  }
+  if (rows.empty() && !with_plan) return nullptr;
+  int64_t n_edges = 0;
+  for (int32_t r : rows) n_edges += rp[r + 1] - rp[r];
 
   // ---- pieces: a row longer than piece_max is cut into equal interleaved pieces
-  const int64_t target = (n_edges + n_units - 1) / n_units;      // edges per unit
+  const int64_t target = std::max<int64_t>(1, (n_edges + n_units - 1) / n_units);      // edges per unit
   int64_t piece_max = std::max<int64_t>(32, target / 3);
   std::vector<int32_t> r_pieces(rows.size()), r_pbase(rows.size()), r_off(rows.size() + 1);
   int64_t n_pieces = 0;
@@ -268,10 +292,12 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   n_windows = (g->num_cols + window_span - 1) / window_span;
   int window_bits = 0;
   while ((1LL << window_bits) < n_windows) ++window_bits;
-  k_sweep_keys<<<(int)ceil_div((int64_t)rows.size() * 32, threads), threads>>>(
-      (int)rows.size(), d_rows.p, d_off.p, d_pbase.p, d_pieces.p, d_code.p, g->rowptr, g->src, g->w_hat, src_bits,
-      window_span, window_bits, keys_in.p, vals_in.p);
-  SWEEP_CUDA(cudaGetLastError());
+  if (!rows.empty()) {
+    k_sweep_keys<<<(int)ceil_div((int64_t)rows.size() * 32, threads), threads>>>(
+        (int)rows.size(), d_rows.p, d_off.p, d_pbase.p, d_pieces.p, d_code.p, g->rowptr, g->src, g->w_hat, src_bits,
+        window_span, window_bits, keys_in.p, vals_in.p);
+    SWEEP_CUDA(cudaGetLastError());
+  }
   int unit_bits = 1;
   while ((1 << unit_bits) < n_units) ++unit_bits;
   const int key_bits = unit_bits + window_bits + kSweepSlotBits;
@@ -279,17 +305,51 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   SWEEP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, vals_out.p,
                                              (int)n_edges, 0, key_bits));
   SWEEP_CUDA(tmp.alloc(tmp_bytes));
-  SWEEP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, vals_out.p,
-                                             (int)n_edges, 0, key_bits));
+  if (n_edges > 0)
+    SWEEP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, vals_out.p,
+                                               (int)n_edges, 0, key_bits));
   const int64_t n_records = n_iters * 32;
   if (n_records > 0) {
     k_sweep_fill<<<(int)ceil_div(n_records, threads), threads>>>(n_records, n_warps, d_warp_ptr.p, d_unit_off.p,
                                                                  vals_out.p, src_bits, (int)((unsigned)S << src_bits), d_rec.p);
     SWEEP_CUDA(cudaGetLastError());
   }
+  // ---- row plan of the other rows (rows.cu): blocks of kRowsBlock consecutive rows, inside a block
+  // the rows ordered by degree (descending) so that the sub-warps of a warp get rows of equal length
+  Dev<uint8_t> d_perm;
+  Dev<int32_t> d_cnt;
+  Dev<int2> d_rec2;
+  int64_t n_blocks = 0;
+  if (with_plan) {
+    n_blocks = (n + kRowsBlock - 1) / kRowsBlock;
+    std::vector<uint8_t> in_sweep((size_t)n, 0);
+    for (int32_t r : rows) in_sweep[r] = 1;
+    std::vector<uint8_t> perm((size_t)n_blocks * kRowsBlock, 0);
+    std::vector<int32_t> cnt((size_t)n_blocks, 0);
+    std::vector<int32_t> bucket_pos(kRowsBlock);
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      const int64_t r0 = b * kRowsBlock, r1 = std::min<int64_t>(n, r0 + kRowsBlock);
+      int c = 0;
+      for (int64_t r = r0; r < r1; ++r)
+        if (!in_sweep[r]) bucket_pos[c++] = (int32_t)(r - r0);
+      std::stable_sort(bucket_pos.begin(), bucket_pos.begin() + c, [&](int32_t a, int32_t bb) {
+        return rp[r0 + a + 1] - rp[r0 + a] > rp[r0 + bb + 1] - rp[r0 + bb];
+      });
+      for (int i = 0; i < c; ++i) perm[(size_t)r0 + i] = (uint8_t)bucket_pos[i];
+      cnt[b] = c;
+    }
+    SWEEP_CUDA(d_perm.upload(perm)); SWEEP_CUDA(d_cnt.upload(cnt));
+    SWEEP_CUDA(d_rec2.alloc((size_t)g->nnz + 8));
+    if (g->nnz > 0) {
+      k_interleave<<<(int)std::min<int64_t>(ceil_div(g->nnz, threads), 148 * 16), threads>>>(g->nnz, g->src, g->w_hat, d_rec2.p);
+      SWEEP_CUDA(cudaGetLastError());
+    }
+  }
   SWEEP_CUDA(cudaDeviceSynchronize());
 
   SweepSched* s = new SweepSched();
+  s->plan.n_blocks = n_blocks; s->plan.num_rows = n;
+  s->plan.perm = d_perm.release(); s->plan.blk_cnt = d_cnt.release(); s->plan.rec = d_rec2.release();
   s->slots = S; s->src_bits = src_bits;
   s->n_ctas = n_sms; s->n_warps = n_warps; s->n_units = n_units;
   s->n_rows = (int64_t)rows.size(); s->n_edges = n_edges; s->n_iters = n_iters;
