@@ -31,20 +31,22 @@ __global__ void k_pair_scores(const float* __restrict__ out, int ld, const int64
   if (lane == 0) score[j] = s;
 }
 
-// One warp per (user, pos, neg) triple.
+// One warp per (user, pos, neg) triple: pair scores, loss terms, and the three gradient rows of
+// d loss / d out written to `rows` ([3 * batch, ld]: row 3t = user, 3t+1 = pos, 3t+2 = neg) with their
+// node ids in `touched`. No atomics: k_bpr_scatter adds the rows to the tables in a fixed order.
 __global__ void k_bpr(int64_t num_nodes, int ld, int64_t batch, const int64_t* __restrict__ users,
                       const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
                       const float* __restrict__ out, const float* __restrict__ e0, float inv_batch,
-                      float decay_over_batch, float alpha0, float* __restrict__ grad_out,
-                      float* __restrict__ grad_e0, int32_t* __restrict__ touched,
+                      float* __restrict__ rows, int32_t* __restrict__ touched,
                       float* __restrict__ per_triple, int* __restrict__ bad) {
   const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= batch) return;
   const int64_t u = users[t], p = pos[t], n = neg[t];
   if (u < 0 || u >= num_nodes || p < 0 || p >= num_nodes || n < 0 || n >= num_nodes) {
+    // the reference raises IndexError / a device assert: flag it (k_bpr_reduce turns the losses into NaN)
     if (lane == 0) { atomicExch(bad, 1); per_triple[2 * t] = 0.f; per_triple[2 * t + 1] = 0.f; }
-    if (touched && lane < 3) touched[3 * t + lane] = 0;
+    if (lane < 3) touched[3 * t + lane] = -1;
     return;
   }
   const int vec = ld / 4;
@@ -71,39 +73,87 @@ __global__ void k_bpr(int64_t num_nodes, int ld, int64_t batch, const int64_t* _
   const float sig = 1.f / (1.f + expf(x));                    // sigmoid(-x)
   const float coef = -sig * inv_batch;                        // d loss / d s+  (= - d loss / d s-)
   if (lane == 0) { per_triple[2 * t] = loss; per_triple[2 * t + 1] = sq; }
-  if (touched && lane < 3) touched[3 * t + lane] = (int32_t)(lane == 0 ? u : (lane == 1 ? p : n));
+  if (lane < 3) touched[3 * t + lane] = (int32_t)(lane == 0 ? u : (lane == 1 ? p : n));
+  float* r0 = rows + (size_t)(3 * t) * ld;
 #pragma unroll
   for (int k = 0; k < kMaxVecPerLane; ++k) {
     const int c = lane + 32 * k;
     if (c < vec) {
-      float4 gu = make_float4(coef * (op[k].x - on[k].x), coef * (op[k].y - on[k].y),
-                              coef * (op[k].z - on[k].z), coef * (op[k].w - on[k].w));
-      float4 gp = make_float4(coef * ou[k].x, coef * ou[k].y, coef * ou[k].z, coef * ou[k].w);
-      float4 gn = make_float4(-gp.x, -gp.y, -gp.z, -gp.w);
-      atomicAdd(reinterpret_cast<float4*>(grad_out + (size_t)u * ld + 4 * c), gu);
-      atomicAdd(reinterpret_cast<float4*>(grad_out + (size_t)p * ld + 4 * c), gp);
-      atomicAdd(reinterpret_cast<float4*>(grad_out + (size_t)n * ld + 4 * c), gn);
-      if (grad_e0) {
-        float4 a = ldg_f4(e0 + (size_t)u * ld + 4 * c), b = ldg_f4(e0 + (size_t)p * ld + 4 * c),
-               d = ldg_f4(e0 + (size_t)n * ld + 4 * c);
-        const float r = decay_over_batch;
-        float4 zu = make_float4(fmaf(alpha0, gu.x, r * a.x), fmaf(alpha0, gu.y, r * a.y),
-                                fmaf(alpha0, gu.z, r * a.z), fmaf(alpha0, gu.w, r * a.w));
-        float4 zp = make_float4(fmaf(alpha0, gp.x, r * b.x), fmaf(alpha0, gp.y, r * b.y),
-                                fmaf(alpha0, gp.z, r * b.z), fmaf(alpha0, gp.w, r * b.w));
-        float4 zn = make_float4(fmaf(alpha0, gn.x, r * d.x), fmaf(alpha0, gn.y, r * d.y),
-                                fmaf(alpha0, gn.z, r * d.z), fmaf(alpha0, gn.w, r * d.w));
-        atomicAdd(reinterpret_cast<float4*>(grad_e0 + (size_t)u * ld + 4 * c), zu);
-        atomicAdd(reinterpret_cast<float4*>(grad_e0 + (size_t)p * ld + 4 * c), zp);
-        atomicAdd(reinterpret_cast<float4*>(grad_e0 + (size_t)n * ld + 4 * c), zn);
-      }
+      const float4 gu = make_float4(coef * (op[k].x - on[k].x), coef * (op[k].y - on[k].y),
+                                    coef * (op[k].z - on[k].z), coef * (op[k].w - on[k].w));
+      const float4 gp = make_float4(coef * ou[k].x, coef * ou[k].y, coef * ou[k].z, coef * ou[k].w);
+      st_f4(r0 + 4 * c, gu);
+      st_f4(r0 + ld + 4 * c, gp);
+      st_f4(r0 + 2 * ld + 4 * c, make_float4(-gp.x, -gp.y, -gp.z, -gp.w));
     }
   }
 }
 
+// grad_out[row] += sum of the gradient rows of `row`; grad_e0[row] += sum of (alpha0 * gradient row +
+// (decay / batch) * e0[row]) -- one term per occurrence, i.e. the layer-0 L2 term with multiplicity
+// (src/utils_v2.py:193-211). Deterministic: one warp per gradient row j; it is the leader of its node
+// if no earlier row carries the same id, and a leader adds all rows of that node in input order
+// (users first, then positives, then negatives of a triple; triples in batch order). The reference's
+// scatter in autograd's index_put backward is likewise sequential on CPU; the round-1 kernel used
+// float4 atomics, whose order changed from run to run. Also marks the node in `row_mask` (bit per
+// row of the tables: the SpMM epilogues skip the addend rows whose bit is clear).
+__global__ void k_bpr_scatter(int n, int ld, const int32_t* __restrict__ touched, const float* __restrict__ rows,
+                              const float* __restrict__ e0, float decay_over_batch, float alpha0,
+                              float* __restrict__ grad_out, float* __restrict__ grad_e0,
+                              uint32_t* __restrict__ row_mask) {
+  const int j = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const int me = touched[j];
+  if (me < 0) return;
+  bool dup = false;
+  for (int q = lane; q < j; q += 32) dup |= (touched[q] == me);
+  if (__any_sync(0xffffffffu, dup)) return;
+  const int vec = ld / 4;
+  float4 g[kMaxVecPerLane], z[kMaxVecPerLane], e[kMaxVecPerLane];
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    g[k] = z[k] = e[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = lane + 32 * k;
+    if (c < vec && grad_e0) e[k] = ldg_f4(e0 + (size_t)me * ld + 4 * c);
+  }
+  const float r = decay_over_batch;
+  for (int base = j; base < n; base += 32) {
+    const int q = base + lane;
+    unsigned hit = __ballot_sync(0xffffffffu, q < n && touched[q] == me);
+    while (hit) {
+      const int rr = base + __ffs(hit) - 1;
+      hit &= hit - 1;
+#pragma unroll
+      for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (c < vec) {
+          const float4 x = ldg_f4(rows + (size_t)rr * ld + 4 * c);
+          g[k] = add4(g[k], x);
+          z[k] = add4(z[k], make_float4(fmaf(alpha0, x.x, r * e[k].x), fmaf(alpha0, x.y, r * e[k].y),
+                                        fmaf(alpha0, x.z, r * e[k].z), fmaf(alpha0, x.w, r * e[k].w)));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < vec) {
+      float* dg = grad_out + (size_t)me * ld + 4 * c;
+      st_f4(dg, add4(ld_f4(dg), g[k]));
+      if (grad_e0) {
+        float* dz = grad_e0 + (size_t)me * ld + 4 * c;
+        st_f4(dz, add4(ld_f4(dz), z[k]));
+      }
+    }
+  }
+  if (row_mask && lane == 0) atomicOr(&row_mask[me >> 5], 1u << (me & 31));
+}
+
 // Deterministic reduction of the per-triple terms (fixed tree, double accumulators).
 __global__ void k_bpr_reduce(const float* __restrict__ per_triple, int64_t batch, double decay,
-                             float* __restrict__ loss3) {
+                             const int* __restrict__ bad, float* __restrict__ loss3) {
   __shared__ double s_loss[256], s_sq[256];
   double a = 0.0, b = 0.0;
   for (int64_t t = threadIdx.x; t < batch; t += 256) { a += per_triple[2 * t]; b += per_triple[2 * t + 1]; }
@@ -116,6 +166,7 @@ __global__ void k_bpr_reduce(const float* __restrict__ per_triple, int64_t batch
   if (threadIdx.x == 0) {
     float bpr = (float)(s_loss[0] / (double)batch);
     float reg = (float)(0.5 * s_sq[0] / (double)batch * decay);
+    if (*bad) bpr = reg = __int_as_float(0x7fc00000);      // an id outside [0, num_nodes): NaN, not a silently biased loss
     loss3[0] = bpr; loss3[1] = reg; loss3[2] = bpr + reg;
   }
 }
@@ -190,15 +241,17 @@ __global__ void k_adam_tail(int64_t beg, int64_t n, float* __restrict__ p, const
 int bpr_launch(int64_t num_nodes, int ld, int64_t batch, const int64_t* users, const int64_t* pos,
                const int64_t* neg, const float* out, const float* e0, double decay, float alpha0,
                float* grad_out, float* grad_e0, int32_t* touched, float* loss3, float* per_triple,
-               int* bad, cudaStream_t st) {
+               float* rows, uint32_t* row_mask, int* bad, cudaStream_t st) {
   const int threads = 256;
-  const int grid = (int)ceil_div(batch * 32, threads);
   ProfScope ps(PROF_BPR, st);
-  k_bpr<<<grid, threads, 0, st>>>(num_nodes, ld, batch, users, pos, neg, out, e0,
-                                  (float)(1.0 / (double)batch), (float)(decay / (double)batch), alpha0,
-                                  grad_out, grad_e0, touched, per_triple, bad);
+  k_bpr<<<(int)ceil_div(batch * 32, threads), threads, 0, st>>>(num_nodes, ld, batch, users, pos, neg, out, e0,
+                                                                (float)(1.0 / (double)batch), rows, touched,
+                                                                per_triple, bad);
   LGC_LAUNCH_CHECK();
-  k_bpr_reduce<<<1, 256, 0, st>>>(per_triple, batch, decay, loss3);
+  k_bpr_scatter<<<(int)ceil_div(batch * 3 * 32, threads), threads, 0, st>>>(
+      (int)(batch * 3), ld, touched, rows, e0, (float)(decay / (double)batch), alpha0, grad_out, grad_e0, row_mask);
+  LGC_LAUNCH_CHECK();
+  k_bpr_reduce<<<1, 256, 0, st>>>(per_triple, batch, decay, bad, loss3);
   LGC_LAUNCH_CHECK();
   return LGC_OK;
 }
@@ -229,8 +282,11 @@ extern "C" int lgc_scatter_add_rows(int64_t n, int ld, const int64_t* idx, const
   return LGC_OK;
 }
 
+// 16 bytes of flags | per-triple terms | touched ids (when the caller passes none) | the 3 * batch
+// gradient rows (sized for the widest supported row, ld = 256)
 extern "C" size_t lgc_bpr_workspace_bytes(int64_t batch) {
-  return (size_t)batch * 2 * sizeof(float) + 16;
+  return 16 + (size_t)batch * 2 * sizeof(float) + (size_t)batch * 3 * sizeof(int32_t) +
+         (size_t)batch * 3 * 128 * kMaxVecPerLane * sizeof(float) + 64;
 }
 
 extern "C" int lgc_bpr_loss_grad(int64_t num_nodes, int ld, int64_t batch, const int64_t* users,
@@ -248,9 +304,11 @@ extern "C" int lgc_bpr_loss_grad(int64_t num_nodes, int ld, int64_t batch, const
   cudaStream_t st = (cudaStream_t)stream;
   int* bad = (int*)workspace;
   float* per_triple = (float*)((char*)workspace + 16);
+  int32_t* own_touched = (int32_t*)(per_triple + batch * 2);
+  float* rows = (float*)(((uintptr_t)(own_touched + batch * 3) + 63) / 64 * 64);
   LGC_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
   int rc = bpr_launch(num_nodes, ld, batch, users, pos, neg, out, e0, decay, alpha0, grad_out, grad_e0,
-                      touched, loss3, per_triple, bad, st);
+                      touched ? touched : own_touched, loss3, per_triple, rows, nullptr, bad, st);
   return rc;
 }
 

@@ -67,16 +67,22 @@ struct EpiPre {
   float q[N][W];
 };
 
+// `addend_on` = false: the addend row is known to be zero (EpiArgs::addend_mask): not read
 template <int MODE, int W>
-__device__ __forceinline__ void epi_preload_w(const EpiArgs& a, size_t off, EpiPre<MODE, W>& p) {
+__device__ __forceinline__ void epi_preload_w(const EpiArgs& a, size_t off, EpiPre<MODE, W>& p,
+                                              bool addend_on = true) {
   if constexpr (MODE == EPI_PLAIN) {
-    if (a.addend) ldv_stream<W>(a.addend + off, p.q[0]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) p.q[0][i] = 0.f;
+    if (a.addend && addend_on) ldv_stream<W>(a.addend + off, p.q[0]);
   } else if constexpr (MODE == EPI_FWD_INIT) {
     ldv_stream<W>(a.xrow + off, p.q[0]);
   } else if constexpr (MODE == EPI_FWD_RMW) {
     ldv_stream<W>(a.acc + off, p.q[0]);
   } else if constexpr (MODE == EPI_ADAM) {
-    ldv_stream<W>(a.addend + off, p.q[0]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) p.q[0][i] = 0.f;
+    if (addend_on) ldv_stream<W>(a.addend + off, p.q[0]);
     ldv_stream<W>(a.p + off, p.q[1]);
     ldv_stream<W>(a.m + off, p.q[2]);
     ldv_stream<W>(a.v + off, p.q[3]);

@@ -15,7 +15,8 @@
 //     broadcast inside the sub-warp with shuffles; the gathers of a row are issued back to back;
 //   * rows are taken in blocks of 256 consecutive rows (all row-stream traffic of a CTA stays inside
 //     a 64 KB window per table) but INSIDE a block in descending-degree order (graph build), so the
-//     4 sub-warps of a warp work on rows of equal length: no power-law divergence, no edge balancing;
+//     4 sub-warps of a warp work on rows of equal length: no power-law divergence, no edge balancing
+//     (a warp-autonomous variant with 32-row blocks held in registers measured 5 % slower);
 //   * no shared-memory tiles: the unified L1 keeps the hot item rows (a few hundred items carry half
 //     of the edges), which takes that traffic off the L2 -> SM path.
 // Edges of a row are added in CSR (= edge-list) order, like the CPU scatter_add_ of the reference.
@@ -25,89 +26,117 @@ namespace lgc {
 namespace {
 
 constexpr int kRowsThreads = 256;
+#ifndef LGC_ROWS_G
+#define LGC_ROWS_G 2
+#endif
+
+// N edges of the current record set (sub-warp lanes t0 .. t0+N-1): all gathers first, then the FMAs in
+// edge order. `n` = edges this sub-warp's row still has (rows of a warp differ by at most a few edges
+// after the degree sort: the shorter ones are predicated off).
+template <int L, int V, int N>
+__device__ __forceinline__ void rows_group(const int2 my, int t0, int n, const float* __restrict__ xl, int ld,
+                                           float4 (&acc)[V]) {
+  float4 xv[N][V];
+  float wv[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const int s = __shfl_sync(0xffffffffu, my.x, t0 + t, L);
+    wv[t] = __int_as_float(__shfl_sync(0xffffffffu, my.y, t0 + t, L));
+    if (t0 + t < n) {
+      const float* xr = xl + (size_t)(unsigned)s * ld;
+#pragma unroll
+      for (int v = 0; v < V; ++v) xv[t][v] = ldg_f4_ptx(xr + 4 * L * v);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t)
+    if (t0 + t < n) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = fma4_packed(wv[t], xv[t][v], acc[v]);
+    }
+}
 
 template <int L, int V, int MODE>
-__global__ void __launch_bounds__(kRowsThreads)
+__global__ void __launch_bounds__(kRowsThreads, (MODE == EPI_ADAM || MODE == EPI_FWD_FINAL || V > 2) ? 3 : 4)
 k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, const uint8_t* __restrict__ perm,
             const int32_t* __restrict__ blk_cnt, int n_blocks, int num_rows, const float* __restrict__ x,
             EpiArgs args) {
-  constexpr int LD = 4 * L * V, NSUB = 32 / L, SUBS = (kRowsThreads / 32) * NSUB, G = L < 4 ? L : 4;
+  constexpr int LD = 4 * L * V, NSUB = 32 / L, SUBS = (kRowsThreads / 32) * NSUB, G = LGC_ROWS_G;
   static_assert(kRowsThreads == kRowsBlock, "one thread loads one row's metadata");
   __shared__ int s_rp[2][kRowsBlock + 1];
   __shared__ uint8_t s_perm[2][kRowsBlock];
+  __shared__ uint32_t s_mask[2][kRowsBlock / 32];      // addend rows that are not zero (all ones: dense addend)
   const int tid = threadIdx.x, lane = tid & 31, wic = tid >> 5, sw = lane / L, sl = lane % L;
   const int sub = wic * NSUB + sw;
   const float* const xl = x + 4 * sl;
   int buf = 0;
+#pragma unroll 1
   for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, buf ^= 1) {
     const int row0 = b * kRowsBlock;
     const int cnt = blk_cnt[b];
     s_rp[buf][tid] = rowptr[min(row0 + tid, num_rows)];
     if (tid == 0) s_rp[buf][kRowsBlock] = rowptr[min(row0 + kRowsBlock, num_rows)];
     s_perm[buf][tid] = perm[row0 + tid];
+    if ((MODE == EPI_PLAIN || MODE == EPI_ADAM) && tid < kRowsBlock / 32)
+      s_mask[buf][tid] = args.addend_mask ? args.addend_mask[(row0 >> 5) + tid] : 0xffffffffu;
     __syncthreads();                                   // two buffers: one barrier per block is enough
-    for (int j0 = 0; j0 < cnt; j0 += SUBS) {
-      const int j = j0 + sub;
-      const bool valid = j < cnt;
-      int e0 = 0, deg = 0, r = row0;
-      if (valid) {
+    // the sub-warp's row of pass j0: (row, first CSR entry, degree) and its first L records, one per
+    // lane -- fetched one pass ahead so that the record latency is off the critical path. Passes
+    // alternate direction (the block's rows are in descending-degree order): every warp gets the
+    // same share of long and short rows, which is what the barrier above waits for.
+    int r_n = row0, e0_n = 0, deg_n = 0;
+    int2 my_n = make_int2(0, 0);
+    auto fetch = [&](int j0, int pass) {
+      const int j = j0 + ((pass & 1) ? SUBS - 1 - sub : sub);
+      r_n = row0; e0_n = 0; deg_n = -1; my_n = make_int2(0, 0);
+      if (j < cnt) {
         const int lr = s_perm[buf][j];
-        r = row0 + lr;
-        e0 = s_rp[buf][lr];
-        deg = s_rp[buf][lr + 1] - e0;
+        r_n = row0 + lr;
+        e0_n = s_rp[buf][lr];
+        deg_n = s_rp[buf][lr + 1] - e0_n;
+        if (sl < deg_n) my_n = __ldg(rec + e0_n + sl);
       }
+    };
+    fetch(0, 0);
+    int pass = 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < cnt; j0 += SUBS, ++pass) {
+      const int r = r_n, e0 = e0_n, deg = deg_n;      // deg < 0: no row for this sub-warp in this pass
+      const bool valid = deg >= 0;
+      int2 my = my_n;
+      fetch(j0 + SUBS, pass + 1);
       const int dmax = __reduce_max_sync(0xffffffffu, deg);
-      int2 my = make_int2(0, 0);                       // first L records of the row, one per lane
-      if (sl < deg) my = __ldg(rec + e0 + sl);
       const size_t off = (size_t)r * LD + 4 * sl;
       EpiPre<MODE, 4> pre[V];
       if (MODE != EPI_FWD_FINAL && valid) {
+        bool addend_on = true;
+        if (MODE == EPI_PLAIN || MODE == EPI_ADAM) addend_on = (s_mask[buf][(r - row0) >> 5] >> (r & 31)) & 1u;
 #pragma unroll
-        for (int v = 0; v < V; ++v) epi_preload_w<MODE, 4>(args, off + 4 * L * v, pre[v]);
+        for (int v = 0; v < V; ++v) epi_preload_w<MODE, 4>(args, off + 4 * L * v, pre[v], addend_on);
       }
-      float acc[V][4];
+      float4 acc[V];
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[v][i] = 0.f;
+      for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
       for (int base = 0; base < dmax; base += L) {
         if (base > 0) {
           my = make_int2(0, 0);
           if (base + sl < deg) my = __ldg(rec + e0 + base + sl);
         }
         const int n = deg - base;                      // edges left in this row (<= 0: none)
-#pragma unroll
-        for (int t0 = 0; t0 < L; t0 += G) {
-          if (base + t0 >= dmax) break;                // warp-uniform
-          float xv[G][V][4], wv[G];
-#pragma unroll
-          for (int t = 0; t < G; ++t) {
-            const int s = __shfl_sync(0xffffffffu, my.x, t0 + t, L);
-            wv[t] = __int_as_float(__shfl_sync(0xffffffffu, my.y, t0 + t, L));
-            if (t0 + t < n) {
-              const float* xr = xl + (size_t)(unsigned)s * LD;
-#pragma unroll
-              for (int v = 0; v < V; ++v) ldv_nc<4>(xr + 4 * L * v, xv[t][v]);
-            } else {
-#pragma unroll
-              for (int v = 0; v < V; ++v)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xv[t][v][i] = 0.f;
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < G; ++t)                  // edge order kept per row
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) acc[v][i] = fmaf(wv[t], xv[t][v][i], acc[v][i]);
+        const int m = min(dmax - base, L);             // warp-uniform: record lanes in use
+#pragma unroll 1
+        for (int t0 = 0; t0 < m; t0 += G) {
+          if (m - t0 >= G) rows_group<L, V, G>(my, t0, n, xl, LD, acc);
+          else rows_group<L, V, 1>(my, t0, n, xl, LD, acc);
         }
       }
       if (valid) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          if (MODE == EPI_FWD_FINAL) epilogue_w<MODE, 4>(args, off + 4 * L * v, acc[v]);
-          else epi_finish_w<MODE, 4>(args, off + 4 * L * v, acc[v], pre[v]);
+          const float s4[4] = {acc[v].x, acc[v].y, acc[v].z, acc[v].w};
+          if (MODE == EPI_FWD_FINAL) epilogue_w<MODE, 4>(args, off + 4 * L * v, s4);
+          else epi_finish_w<MODE, 4>(args, off + 4 * L * v, s4, pre[v]);
         }
       }
     }

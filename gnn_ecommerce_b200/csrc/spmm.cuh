@@ -26,6 +26,9 @@ struct EpiArgs {
   float* acc = nullptr;
   const float* xrow = nullptr;
   const float* addend = nullptr;
+  // optional: bit r set <=> row r of `addend` may be non-zero (the sparse gradient tables of the
+  // training step: <= 3 * batch rows). The rows kernel skips the addend stream of the other rows.
+  const uint32_t* addend_mask = nullptr;
   float a0 = 0.f, a1 = 0.f, scale = 1.f, beta = 0.f;
   float* p = nullptr;
   float* m = nullptr;

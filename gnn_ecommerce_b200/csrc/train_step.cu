@@ -13,7 +13,7 @@ namespace lgc {
 int bpr_launch(int64_t num_nodes, int ld, int64_t batch, const int64_t* users, const int64_t* pos,
                const int64_t* neg, const float* out, const float* e0, double decay, float alpha0,
                float* grad_out, float* grad_e0, int32_t* touched, float* loss3, float* per_triple,
-               int* bad, cudaStream_t st);
+               float* rows, uint32_t* row_mask, int* bad, cudaStream_t st);
 
 namespace {
 
@@ -21,7 +21,8 @@ struct StepLayout {
   size_t t;              // floats per table
   int n_x;               // scratch tables: the forward's stored layers, reused by the backward
   float* xs[kMaxHist];
-  float *out, *g, *z, *partials, *per_triple;
+  float *out, *g, *z, *partials, *per_triple, *rows;
+  uint32_t* mask;        // bit per table row: set for the rows of G / Z that are not zero
   int32_t* touched;
   int* bad;
   size_t bytes;
@@ -37,22 +38,25 @@ StepLayout layout(const lgc_graph* g, int ld, int num_layers, int64_t batch, voi
   auto take = [&](size_t bytes) { char* q = p ? p + off : nullptr; off += align_up(bytes, 256); return q; };
   L.g = (float*)take(L.t * 4);          // G and Z first: lgc_train_workspace_init zeroes them
   L.z = (float*)take(L.t * 4);
+  L.mask = (uint32_t*)take(((size_t)g->num_nodes + 31) / 32 * 4 + 64);   // right behind G and Z: zeroed with them
   L.n_x = num_layers > 1 ? num_layers - 1 : 0;
   for (int i = 0; i < kMaxHist; ++i) L.xs[i] = i < L.n_x ? (float*)take(L.t * 4) : nullptr;
   L.out = (float*)take(L.t * 4);
   L.partials = (float*)take(spmm_partials_floats(g, ld) * 4);
   L.per_triple = (float*)take((size_t)batch * 2 * 4);
   L.touched = (int32_t*)take((size_t)batch * 3 * 4);
+  L.rows = (float*)take((size_t)batch * 3 * ld * 4);
   L.bad = (int*)take(16);
   L.bytes = off;
   return L;
 }
 
 __global__ void k_zero_rows(const int32_t* __restrict__ rows, int64_t n_rows, int ld,
-                            float* __restrict__ a, float* __restrict__ b) {
+                            float* __restrict__ a, float* __restrict__ b, uint32_t* __restrict__ mask) {
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (i >= n_rows) return;
+  if (i >= n_rows || rows[i] < 0) return;
+  if (lane == 0) mask[rows[i] >> 5] = 0u;             // every set bit of the word belongs to a touched row
   const size_t base = (size_t)rows[i] * ld;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = lane; c < ld / 4; c += 32) {
@@ -87,7 +91,8 @@ extern "C" int lgc_train_workspace_init(const lgc_graph_t* g, int ld, int num_la
     return LGC_ERR_WORKSPACE;
   }
   StepLayout L = layout(g, ld, num_layers, batch, workspace);
-  LGC_CUDA(cudaMemsetAsync(L.g, 0, 2 * ((L.t * 4 + 255) / 256 * 256), (cudaStream_t)stream));
+  LGC_CUDA(cudaMemsetAsync(L.g, 0, (size_t)((char*)L.mask - (char*)L.g) + ((size_t)g->num_nodes + 31) / 32 * 4 + 64,
+                           (cudaStream_t)stream));
   return LGC_OK;
 }
 
@@ -122,7 +127,7 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
   // ---- loss + sparse gradients (src/lightgcn.py:123-125,279-286; src/utils_v2.py:193-211)
   LGC_CUDA(cudaMemsetAsync(L.bad, 0, sizeof(int), st));
   rc = bpr_launch(g->num_nodes, ld, a->batch, a->users, a->pos, a->neg, L.out, a->e0, a->decay, alpha[0],
-                  L.g, L.z, L.touched, a->loss3, L.per_triple, L.bad, st);
+                  L.g, L.z, L.touched, a->loss3, L.per_triple, L.rows, L.mask, L.bad, st);
   if (rc) return rc;
 
   // ---- backward (Horner) + Adam (src/train_lightgcn.py:146-147)
@@ -140,6 +145,7 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
       e.scale = scale;
       e.beta = alpha[l];
       e.addend = L.g;
+      e.addend_mask = L.mask;
       rc = launch_spmm(g, ld, cur, EPI_PLAIN, e, L.partials, st);
       if (rc) return rc;
       cur = tmp[flip];
@@ -149,12 +155,13 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
     EpiArgs e;                                   // gE0 = Z + A h_1, consumed by Adam in place
     e.scale = scale;
     e.addend = L.z;
+    e.addend_mask = L.mask;
     e.p = a->e0; e.m = a->m; e.v = a->v;
     e.adam = as;
     rc = launch_spmm(g, ld, cur, EPI_ADAM, e, L.partials, st);
     if (rc) return rc;
   }
-  k_zero_rows<<<(int)ceil_div(a->batch * 3 * 32, 256), 256, 0, st>>>(L.touched, a->batch * 3, ld, L.g, L.z);
+  k_zero_rows<<<(int)ceil_div(a->batch * 3 * 32, 256), 256, 0, st>>>(L.touched, a->batch * 3, ld, L.g, L.z, L.mask);
   LGC_LAUNCH_CHECK();
   return LGC_OK;
 }
