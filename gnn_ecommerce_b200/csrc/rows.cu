@@ -38,11 +38,13 @@ __device__ __forceinline__ void rows_group(const int2 my, int t0, int n, const f
                                            float4 (&acc)[V]) {
   float4 xv[N][V];
   float wv[N];
+  bool ok[N];
 #pragma unroll
   for (int t = 0; t < N; ++t) {
     const int s = __shfl_sync(0xffffffffu, my.x, t0 + t, L);
     wv[t] = __int_as_float(__shfl_sync(0xffffffffu, my.y, t0 + t, L));
-    if (t0 + t < n) {
+    ok[t] = t0 + t < n && s >= 0;                      // s < 0: source row known to be zero (x_mask)
+    if (ok[t]) {
       const float* xr = xl + (size_t)(unsigned)s * ld;
 #pragma unroll
       for (int v = 0; v < V; ++v) xv[t][v] = ldg_f4_ptx(xr + 4 * L * v);
@@ -50,13 +52,13 @@ __device__ __forceinline__ void rows_group(const int2 my, int t0, int n, const f
   }
 #pragma unroll
   for (int t = 0; t < N; ++t)
-    if (t0 + t < n) {
+    if (ok[t]) {
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[v] = fma4_packed(wv[t], xv[t][v], acc[v]);
     }
 }
 
-template <int L, int V, int MODE>
+template <int L, int V, int MODE, bool XM>   // XM: args.x_mask marks the source rows that are not zero
 __global__ void __launch_bounds__(kRowsThreads, (MODE == EPI_ADAM || MODE == EPI_FWD_FINAL || V > 2) ? 3 : 4)
 k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, const uint8_t* __restrict__ perm,
             const int32_t* __restrict__ blk_cnt, int n_blocks, int num_rows, const float* __restrict__ x,
@@ -94,7 +96,10 @@ k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, co
         r_n = row0 + lr;
         e0_n = s_rp[buf][lr];
         deg_n = s_rp[buf][lr + 1] - e0_n;
-        if (sl < deg_n) my_n = __ldg(rec + e0_n + sl);
+        if (sl < deg_n) {
+          my_n = __ldg(rec + e0_n + sl);
+          if (XM && !((args.x_mask[my_n.x >> 5] >> (my_n.x & 31)) & 1u)) my_n.x = -1;
+        }
       }
     };
     fetch(0, 0);
@@ -121,7 +126,10 @@ k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, co
       for (int base = 0; base < dmax; base += L) {
         if (base > 0) {
           my = make_int2(0, 0);
-          if (base + sl < deg) my = __ldg(rec + e0 + base + sl);
+          if (base + sl < deg) {
+            my = __ldg(rec + e0 + base + sl);
+            if (XM && !((args.x_mask[my.x >> 5] >> (my.x & 31)) & 1u)) my.x = -1;
+          }
         }
         const int n = deg - base;                      // edges left in this row (<= 0: none)
         const int m = min(dmax - base, L);             // warp-uniform: record lanes in use
@@ -143,16 +151,16 @@ k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, co
   }
 }
 
-template <int L, int V, int MODE>
-int launch_rows_lvm(const RowPlan* p, const float* x, const EpiArgs& a, const int32_t* rowptr, cudaStream_t st) {
+template <int L, int V, int MODE, bool XM>
+int launch_rows_lvmx(const RowPlan* p, const float* x, const EpiArgs& a, const int32_t* rowptr, cudaStream_t st) {
   static int occ_dev[64] = {};
   int dev = 0;
   LGC_CUDA(cudaGetDevice(&dev));
   int occ = (dev >= 0 && dev < 64) ? occ_dev[dev] : 0;
   static int sms_dev[64] = {};
   if (!occ) {
-    LGC_CUDA(cudaFuncSetAttribute(k_spmm_rows<L, V, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));   // ~36 KB of shared memory, the rest L1
-    LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_rows<L, V, MODE>, kRowsThreads, 0));
+    LGC_CUDA(cudaFuncSetAttribute(k_spmm_rows<L, V, MODE, XM>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));   // ~36 KB of shared memory, the rest L1
+    LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_rows<L, V, MODE, XM>, kRowsThreads, 0));
     if (occ < 1) occ = 1;
     int sms = 0;
     LGC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -163,9 +171,16 @@ int launch_rows_lvm(const RowPlan* p, const float* x, const EpiArgs& a, const in
   const int grid = (int)std::min<int64_t>((int64_t)sms * occ, p->n_blocks);
   if (grid <= 0) return LGC_OK;
   ProfScope ps(PROF_LIGHT + (MODE & 3), st);
-  k_spmm_rows<L, V, MODE><<<grid, kRowsThreads, 0, st>>>(rowptr, p->rec, p->perm, p->blk_cnt, (int)p->n_blocks,
+  k_spmm_rows<L, V, MODE, XM><<<grid, kRowsThreads, 0, st>>>(rowptr, p->rec, p->perm, p->blk_cnt, (int)p->n_blocks,
                                                          (int)p->num_rows, x, a);
   return LGC_OK;
+}
+
+template <int L, int V, int MODE>
+int launch_rows_lvm(const RowPlan* p, const float* x, const EpiArgs& a, const int32_t* rowptr, cudaStream_t st) {
+  if ((MODE == EPI_PLAIN || MODE == EPI_ADAM) && a.x_mask)
+    return launch_rows_lvmx<L, V, MODE, (MODE == EPI_PLAIN || MODE == EPI_ADAM)>(p, x, a, rowptr, st);
+  return launch_rows_lvmx<L, V, MODE, false>(p, x, a, rowptr, st);
 }
 
 template <int L, int V>

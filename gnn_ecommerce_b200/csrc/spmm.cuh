@@ -29,6 +29,9 @@ struct EpiArgs {
   // optional: bit r set <=> row r of `addend` may be non-zero (the sparse gradient tables of the
   // training step: <= 3 * batch rows). The rows kernel skips the addend stream of the other rows.
   const uint32_t* addend_mask = nullptr;
+  // optional: bit s set <=> row s of the GATHERED table x may be non-zero (first backward layer: x is
+  // the sparse gradient table itself). The sweep and the rows kernel skip the gathers of the other rows.
+  const uint32_t* x_mask = nullptr;
   float a0 = 0.f, a1 = 0.f, scale = 1.f, beta = 0.f;
   float* p = nullptr;
   float* m = nullptr;

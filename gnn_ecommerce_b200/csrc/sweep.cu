@@ -179,7 +179,7 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   SWEEP_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   const int n_warps = n_sms * kSweepWarps, n_units = 2 * n_warps;
   const int src_bits = kSweepSrcBits;
-  if (g->num_cols > (1LL << src_bits) || S > kSweepMaxSlots) return nullptr;
+  if (g->num_cols >= (1LL << src_bits) || S > kSweepMaxSlots) return nullptr;   // all-ones source = "skip" marker
 
   const int64_t n = g->num_nodes;
   std::vector<int32_t> rp((size_t)n + 1);
@@ -370,7 +370,27 @@ struct SweepCfg {
   static constexpr int U = U0 < 2 ? 2 : U0;
 };
 
-template <int FPL, int MODE>
+// acc += w * x over a lane's FPL floats; packed FFMA2 (same roundings as fmaf, half the issue slots)
+template <int FPL>
+__device__ __forceinline__ void fma_row(float w, const float (&x)[FPL], float (&acc)[FPL]) {
+  if constexpr (FPL % 2 == 0) {
+    unsigned long long ww;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+#pragma unroll
+    for (int i = 0; i < FPL; i += 2) {
+      unsigned long long xx, aa;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x[i]), "f"(x[i + 1]));
+      asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(acc[i]), "f"(acc[i + 1]));
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(aa) : "l"(ww), "l"(xx));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i]), "=f"(acc[i + 1]) : "l"(aa));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < FPL; ++i) acc[i] = fmaf(w, x[i], acc[i]);
+  }
+}
+
+template <int FPL, int MODE, bool XM>   // XM: args.x_mask marks the source rows that are not zero
 __global__ void __launch_bounds__(32 * kSweepWarps, 1)
 k_spmm_sweep(const int32_t* __restrict__ warp_ptr, const int2* __restrict__ rec, const int2* __restrict__ unit_rows,
              int S, int src_bits, const float* __restrict__ x, float* __restrict__ partials, EpiArgs args) {
@@ -394,7 +414,6 @@ k_spmm_sweep(const int32_t* __restrict__ warp_ptr, const int2* __restrict__ rec,
   const int it0 = warp_ptr[warp], it1 = warp_ptr[warp + 1];
   const unsigned src_mask = (1u << src_bits) - 1u;
   const float* const xl = x + W * l16;
-  const int base_lane = lane & 16;
   float acc[FPL];                                      // sum of the current run of one output row
 #pragma unroll
   for (int i = 0; i < FPL; ++i) acc[i] = 0.f;
@@ -404,12 +423,24 @@ k_spmm_sweep(const int32_t* __restrict__ warp_ptr, const int2* __restrict__ rec,
   // slower). With the table L2-resident the kernel runs only 20 % faster (0.091 vs 0.114 ms for the
   // item rows at c2): it moves 1.1 GB of gathered rows from L2 to the SMs at ~12 TB/s, the measured
   // L2 -> SM ceiling, so hiding the HBM misses has little left to win.
+  // records of one iteration, one per lane; a source row that is known to be zero (x_mask, the
+  // sparse gradient table of the first backward layer) is marked with the all-ones source id
+  const uint32_t* const x_mask = args.x_mask;
+  auto load_rec = [&](int i) {
+    int2 q = __ldg(rec + (size_t)i * 32 + lane);
+    if (XM) {
+      const unsigned s = (unsigned)q.x & src_mask;
+      if (!((x_mask[s >> 5] >> (s & 31)) & 1u)) q.x |= (int)src_mask;
+    }
+    return q;
+  };
   int2 r = make_int2(0, 0);
-  if (it0 < it1) r = __ldg(rec + (size_t)it0 * 32 + lane);
+  if (it0 < it1) r = load_rec(it0);
+  const int base_lane = lane & 16;
 #pragma unroll 1
   for (int it = it0; it < it1; ++it) {
     int2 rn = r;
-    if (it + 1 < it1) rn = __ldg(rec + (size_t)(it + 1) * 32 + lane);   // next iteration's records
+    if (it + 1 < it1) rn = load_rec(it + 1);             // next iteration's records
 #pragma unroll
     for (int b = 0; b < 16; b += U) {
       float xv[U][FPL];
@@ -417,15 +448,20 @@ k_spmm_sweep(const int32_t* __restrict__ warp_ptr, const int2* __restrict__ rec,
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         ev[u] = (unsigned)__shfl_sync(0xffffffffu, r.x, base_lane + b + u);
-        const float* xr = xl + (size_t)(ev[u] & src_mask) * LD;
+        const unsigned sidx = ev[u] & src_mask;
+        if (!XM || sidx != src_mask) {
+          const float* xr = xl + (size_t)sidx * LD;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) ldv_nc<W>(xr + 16 * W * k, &xv[u][W * k]);
+          for (int k = 0; k < NV; ++k) ldv_nc<W>(xr + 16 * W * k, &xv[u][W * k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < FPL; ++i) xv[u][i] = 0.f;
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float wv = __int_as_float(__shfl_sync(0xffffffffu, r.y, base_lane + b + u));
-#pragma unroll
-        for (int i = 0; i < FPL; ++i) acc[i] = fmaf(wv, xv[u][i], acc[i]);
+        fma_row<FPL>(wv, xv[u], acc);
         if ((int)ev[u] < 0) {                          // end of the run: add it to the row's accumulator
           float* a = my + ((ev[u] & 0x7fffffffu) >> src_bits) * LD;
 #pragma unroll
@@ -459,22 +495,29 @@ k_spmm_sweep(const int32_t* __restrict__ warp_ptr, const int2* __restrict__ rec,
   }
 }
 
-template <int FPL, int MODE>
-int launch_sweep_fm(const SweepSched* s, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
+template <int FPL, int MODE, bool XM>
+int launch_sweep_fmx(const SweepSched* s, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
   constexpr int LD = 16 * FPL;
   const size_t smem = (size_t)kSweepUnitsPerCta * (s->slots + 1) * LD * 4;
   static bool attr_set[64] = {};
   int dev = 0;
   LGC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    LGC_CUDA(cudaFuncSetAttribute(k_spmm_sweep<FPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LGC_CUDA(cudaFuncSetAttribute(k_spmm_sweep<FPL, MODE, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSweepSmemBudget));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   ProfScope ps(PROF_HEAVY + (MODE & 3), st);
-  k_spmm_sweep<FPL, MODE><<<s->n_ctas, 32 * kSweepWarps, smem, st>>>(s->warp_ptr, s->rec, s->unit_rows, s->slots,
-                                                                      s->src_bits, x, partials, a);
+  k_spmm_sweep<FPL, MODE, XM><<<s->n_ctas, 32 * kSweepWarps, smem, st>>>(s->warp_ptr, s->rec, s->unit_rows, s->slots,
+                                                                          s->src_bits, x, partials, a);
   return LGC_OK;
+}
+template <int FPL, int MODE>
+int launch_sweep_fm(const SweepSched* s, const float* x, const EpiArgs& a, float* partials, cudaStream_t st) {
+  // the source-mask variant exists for the two epilogues the first backward layer can have
+  if ((MODE == EPI_PLAIN || MODE == EPI_ADAM) && a.x_mask)
+    return launch_sweep_fmx<FPL, MODE, (MODE == EPI_PLAIN || MODE == EPI_ADAM)>(s, x, a, partials, st);
+  return launch_sweep_fmx<FPL, MODE, false>(s, x, a, partials, st);
 }
 
 template <int FPL>

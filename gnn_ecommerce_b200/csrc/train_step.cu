@@ -146,6 +146,7 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
       e.beta = alpha[l];
       e.addend = L.g;
       e.addend_mask = L.mask;
+      if (cur == L.g) e.x_mask = L.mask;        // first backward layer gathers from G itself
       rc = launch_spmm(g, ld, cur, EPI_PLAIN, e, L.partials, st);
       if (rc) return rc;
       cur = tmp[flip];
@@ -156,6 +157,7 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
     e.scale = scale;
     e.addend = L.z;
     e.addend_mask = L.mask;
+    if (cur == L.g) e.x_mask = L.mask;
     e.p = a->e0; e.m = a->m; e.v = a->v;
     e.adam = as;
     rc = launch_spmm(g, ld, cur, EPI_ADAM, e, L.partials, st);
