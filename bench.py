@@ -14,9 +14,11 @@ through the public Python API with pinned host triples copied H2D and the three 
 back D2H every step. Also reported: epoch seconds (122 steps), top-20 scoring users/s (c4),
 the roofline of the dominant kernel, and the CPU port of the reference timed on this box.
 
-`--impl reference` times the reference's CPU path (oracle port: the reference's own torch ops;
-real PyG is not installable here) on all host cores: each step = one LGConv layer forward +
-backward over the same c2 graph (a bounded sample: a full CPU step is ~14 s).
+`--impl reference` times the SAME step (K-layer forward, BPR + L2, backward, dense Adam on the same
+graph and triples) with the reference's own CPU code on all host cores: the reference's `LightGCN`,
+`BPRLoss` and `utils_v2` imported unmodified from the staged copy `oracle/_ref` (only the absent
+third-party `LGConv` operator is the op-for-op restatement of `oracle/lgconv.py`; real PyG is not
+installable here), else the oracle port. One CPU step at c2 is ~5 s on the box's 16 cores.
 """
 from __future__ import annotations
 
@@ -138,11 +140,36 @@ def algorithmic_bytes(g, dim_ld: int, layers: int, nnz: int):
     return {"I": idx, "T": t, "B_prop": b_prop, "step": 2 * b_prop + 7 * t}
 
 
+def workload_name(config: str, g, dim: int, layers: int) -> str:
+    """Same string in both arms (the driver compares them)."""
+    return (f"{config}: LightGCN K={layers} d={dim}, N={g.num_nodes}, nnz={2 * g.num_edges}, "
+            f"batch={BATCH}, full training step (fwd+BPR+bwd+Adam)")
+
+
+def stream_counts(layers: int):
+    """Row streams of the epilogue per launch of a K-layer step (csrc/train_step.cu), SURVEY 8(d)
+    accounting: forward K-1 x PLAIN (layer table written) + FWD_FINAL (K stored tables read, out
+    written); backward K-1 x PLAIN + addend (read + write) + ADAM (addend, p, m, v read; p, m, v
+    written)."""
+    k = max(1, layers)
+    return [1] * (k - 1) + [k + 1] + [2] * (k - 1) + [7]
+
+
+def kernel_bytes(plan, num_nodes: int, ld: int, layers: int):
+    """Algorithmic bytes of ONE launch of each SpMM kernel class, averaged over the 2K launches of a
+    step: 8 B per edge (int32 source + fp32 weight), 4 B rowptr per row, every distinct gathered
+    source row once (ld*4 B), plus the row streams of the fused epilogue (mode dependent)."""
+    rb = ld * 4
+    streams = stream_counts(layers)
+    epi = rb * sum(streams) / float(len(streams))
+    rows = plan.rows_edges * 8 + plan.rows_rows * 4 + plan.rows_sources * rb + plan.rows_rows * epi
+    sweep = plan.sweep_edges * 8 + plan.sweep_rows * 4 + plan.sweep_sources * rb + plan.sweep_rows * epi
+    return {"rows": rows, "sweep": sweep}
+
+
 def light_kernel_bytes(g, graph, ld: int, layers: int = 3):
-    """Algorithmic bytes of ONE launch of the dominant kernel (k_spmm_light, the sub-warp-per-row
-    pass over rows with in-degree <= 32), averaged over the 2K launches of a K-layer step:
-    indices + weights of the light rows' edges, each distinct gathered source row once, rowptr,
-    plus the epilogue traffic of the light rows (mode dependent)."""
+    """Round-1 kernels (no sweep plan for this row width): algorithmic bytes of one launch of
+    k_spmm_light, averaged over the 2K launches of a K-layer step."""
     a = graph.arrays()
     rowptr = a["rowptr"].cpu().numpy().astype(np.int64)
     deg = np.diff(rowptr)
@@ -154,70 +181,84 @@ def light_kernel_bytes(g, graph, ld: int, layers: int = 3):
     rb = ld * 4
     n_light = int(light.sum())
     gather = e_light * 8 + (g.num_nodes + 1) * 4 + distinct_src * rb
-    # one step (csrc/train_step.cu): forward K-1 x PLAIN (1 row stream each: the layer table written) and
-    # FWD_FINAL (K hist tables read + out written); backward K-1 x PLAIN + addend (read + write) and ADAM
-    # (addend, p, m, v read; p, m, v written)
-    k = max(1, layers)
-    streams = [1] * (k - 1) + [k + 1] + [2] * (k - 1) + [7]
+    streams = stream_counts(layers)
     epi = rb * sum(streams) / float(len(streams))
     return {"bytes_per_launch": gather + n_light * epi, "light_rows": n_light,
             "light_edges": e_light, "distinct_sources": distinct_src}
 
 
 # ----------------------------------------------------------------------------- CPU legs
+class CpuStepper:
+    """One full reference training step per call on the host cores: the reference's own classes
+    through `oracle/reference_shim.py` when its sources are available (kind "reference"), else the
+    oracle port (kind "port")."""
+
+    def __init__(self, g, dim, layers, init):
+        import torch
+        from oracle import port, reference_shim
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.torch, self.port = torch, port
+        self.ei, self.ew = port.df_to_graph(g.user, g.item, g.weight)
+        self.ref_utils = None
+        if reference_shim.reference_available():
+            ref_lightgcn, self.ref_utils = reference_shim.load_reference()
+            self.model = ref_lightgcn.LightGCN(g.num_nodes, dim, layers)
+            self.kind = "reference"
+            self.what = ("the reference's own LightGCN / BPRLoss / utils_v2 (staged unmodified under oracle/_ref) "
+                         "around the op-for-op LGConv restatement (PyG itself is not installable here)")
+            self._step = reference_shim.reference_train_step
+        else:
+            self.model = port.PortLightGCN(g.num_nodes, dim, layers)
+            self.kind = "port"
+            self.what = "oracle port of the reference's torch ops"
+        with torch.no_grad():
+            self.model.embedding.weight.copy_(torch.from_numpy(init))
+        self.opt = torch.optim.Adam(self.model.parameters(), LR)
+        self.cores = torch.get_num_threads()
+
+    def step(self, triple):
+        u, p, n = (self.torch.from_numpy(x) for x in triple)
+        if self.ref_utils is not None:
+            return self._step(self.ref_utils, self.model, self.opt, self.ei, self.ew, u, p, n, DECAY)
+        return self.port.train_step(self.model, self.opt, self.ei, self.ew, u, p, n, DECAY)
+
+
 def cpu_full_step(g, dim, layers, init, triple):
-    """One full reference training step on the host cores (oracle port)."""
-    import torch
-    from oracle import port
-    torch.set_num_threads(os.cpu_count() or 1)
-    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
-    model = port.PortLightGCN(g.num_nodes, dim, layers)
-    with torch.no_grad():
-        model.embedding.weight.copy_(torch.from_numpy(init))
-    opt = torch.optim.Adam(model.parameters(), LR)
-    u, p, n = (torch.from_numpy(x) for x in triple)
+    """One full reference training step on the host cores -> (seconds, cores, kind, what)."""
+    st = CpuStepper(g, dim, layers, init)
     t0 = time.perf_counter()
-    port.train_step(model, opt, ei, ew, u, p, n, DECAY)
-    dt = time.perf_counter() - t0
-    return dt, torch.get_num_threads()
+    st.step(triple)
+    return time.perf_counter() - t0, st.cores, st.kind, st.what
 
 
 def reference_arm(args):
-    """`--impl reference`: the reference's CPU arithmetic for the path, all host threads."""
-    import torch
+    """`--impl reference`: the same full training step on the host CPU, all host threads, exactly
+    `--warmup` + `--steps` steps (rank 0 only under torchrun)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import port
-    from oracle.lgconv import LGConv
-    torch.set_num_threads(os.cpu_count() or 1)
-    g, dim, layers, init, _ = make_workload(args.config, 0)
-    ei, ew = port.df_to_graph(g.user, g.item, g.weight)
-    nnz = ei.size(1)
-    conv = LGConv()
-    x = torch.from_numpy(init).requires_grad_(True)
-
-    def one():
-        x.grad = None
-        conv(x, ei, ew).sum().backward()
-
-    for _ in range(args.warmup):
-        one()
+    n_batches = args.steps + args.warmup
+    g, dim, layers, init, triples = make_workload(args.config, n_batches)
+    nnz = 2 * g.num_edges
+    st = CpuStepper(g, dim, layers, init)
+    for i in range(args.warmup):
+        st.step(triples[i])
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one()
+    for i in range(args.steps):
+        losses = st.step(triples[args.warmup + i])
     dt = time.perf_counter() - t0
-    value = nnz * 2 * args.steps / dt / 1e9
-    sample = (f"one LGConv layer forward+backward per step over the full {args.config} graph "
-              f"(nnz={nnz}, d={dim}); a full K={layers} step is {layers}x this plus Adam")
+    value = nnz * 2 * layers * args.steps / dt / 1e9
+    sample = (f"{args.steps} full training steps (K={layers} fwd + BPR + bwd + dense Adam) over the whole "
+              f"{args.config} graph, {dt / args.steps:.2f} s per step; {st.what}")
     line = {"impl": "reference", "metric": "lgconv_gedges_per_s", "value": value, "unit": "GEdges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak" if args.gpus == 1 else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: LightGCN K={layers} d={dim}, N={g.num_nodes}, "
-                                   f"nnz={nnz}, batch={BATCH}"},
-            "cpu_baseline": {"value": value, "unit": "GEdges/s", "cores": torch.get_num_threads(),
-                             "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(args.config, g, dim, layers)},
+            "losses_last_step": [float(x) for x in losses],
+            "cpu_baseline": {"value": value, "unit": "GEdges/s", "cores": st.cores, "kind": st.kind,
+                             "sample": sample},
             "e2e": {"value": value, "unit": "GEdges/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     emit(line)
@@ -234,6 +275,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the measured epoch (sampler + steps + eval)")
     ap.add_argument("--only-scoring", action="store_true", help="skip the training-step timing (dev aid)")
     ap.add_argument("--score-users", type=int, default=0, help="0 = all users (c4)")
     ap.add_argument("--shard-mode", default="auto", choices=["auto", "bipartite", "rows"],
@@ -387,6 +429,16 @@ def main():
             log(f"[bench] scoring failed: {e!r}")
             score = {"error": repr(e)}
 
+    # ---- one measured epoch through the public API (single GPU): device sampler -> n_batch fused
+    # steps -> top-20 of all evaluation users -> recall@20 (src/train_lightgcn.py:79-121,155-162)
+    epoch = None
+    if world == 1 and not args.no_epoch:
+        try:
+            epoch = bench_epoch(model, trainer, ei, ew, g, dev, dim)
+        except Exception as e:
+            log(f"[bench] measured epoch failed: {e!r}")
+            epoch = {"error": repr(e)}
+
     if rank != 0:
         return finish(world, trainer)
 
@@ -396,22 +448,40 @@ def main():
                 "bpr": ms_arr[12] / args.steps}
     step_gbs = alg["step"] / (ms_step * 1e-3) / 1e9
     if world == 1:
-        lk = light_kernel_bytes(g, graph, ld, layers)
-        achieved = lk["bytes_per_launch"] / (light_avg_ms * 1e-3) / 1e9
+        plan = _capi.PlanInfo()
+        _capi.check(lib.lgc_graph_plan_info(graph.handle, ld, C.byref(plan)), "lgc_graph_plan_info")
         traffic = None
-        prof_json = os.path.join(ROOT, "profiles", "ncu_light_traffic.json")
-        if os.path.exists(prof_json):
-            try:
+        if plan.has_plan and plan.rows_rows > 0:
+            # dominant kernel: k_spmm_rows (the low-degree rows: the users); the sweep is reported beside it
+            kb = kernel_bytes(plan, g.num_nodes, ld, layers)
+            kname, kbytes = "k_spmm_rows", kb["rows"]
+            sweep_avg_ms = heavy_ms / max(sum(cnt_arr[t] for t in range(4, 8)), 1)
+            extra = {"sweep_kernel": {"kernel": "k_spmm_sweep", "kernel_ms": sweep_avg_ms,
+                                      "algorithmic_bytes_per_launch": kb["sweep"],
+                                      "achieved": kb["sweep"] / (sweep_avg_ms * 1e-3) / 1e9,
+                                      "frac": kb["sweep"] / (sweep_avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                      "rows": int(plan.sweep_rows), "edges": int(plan.sweep_edges),
+                                      "distinct_sources": int(plan.sweep_sources)},
+                     "rows_kernel": {"rows": int(plan.rows_rows), "edges": int(plan.rows_edges),
+                                     "distinct_sources": int(plan.rows_sources)}}
+            prof_json = os.path.join(ROOT, "profiles", "ncu_rows_traffic.json")
+        else:
+            lk = light_kernel_bytes(g, graph, ld, layers)
+            kname, kbytes, extra = "k_spmm_light", lk["bytes_per_launch"], {}
+            prof_json = os.path.join(ROOT, "profiles", "ncu_light_traffic.json")
+        if os.path.exists(prof_json) and args.config == "c2":
+            try:   # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (c2)
                 traffic = float(json.load(open(prof_json))["dram_bytes_per_launch"])
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_spmm_light", "achieved": achieved, "peak": pk["hbm_gbs"],
+        achieved = kbytes / (light_avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                     "peak_source": pk["source"], "kernel_ms": light_avg_ms,
                     "kernel_share_of_step": light_ms / max(kernel_ms_total, 1e-9),
-                    "algorithmic_bytes_per_launch": lk["bytes_per_launch"],
+                    "algorithmic_bytes_per_launch": kbytes,
                     "step_algorithmic_bytes": alg["step"], "step_achieved_gbs": step_gbs,
-                    "step_frac": step_gbs / pk["hbm_gbs"], "class_ms_per_step": class_ms}
+                    "step_frac": step_gbs / pk["hbm_gbs"], "class_ms_per_step": class_ms, **extra}
     else:
         # whole step against N x the HBM peak (the collectives add NVLink time on top of it)
         if shard_kind == "BipartiteShardedTrainer":
@@ -428,10 +498,10 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        dt, cores = cpu_full_step(g, dim, layers, init, triples[0])
-        cpu = {"value": nnz * 2 * layers / dt / 1e9, "unit": "GEdges/s", "cores": cores, "kind": "port",
+        dt, cores, kind, what = cpu_full_step(g, dim, layers, init, triples[0])
+        cpu = {"value": nnz * 2 * layers / dt / 1e9, "unit": "GEdges/s", "cores": cores, "kind": kind,
                "sample": f"1 full training step (K={layers} fwd + BPR + bwd + dense Adam) at {args.config} "
-                         f"shape, {dt:.1f} s, oracle port of the reference's torch ops",
+                         f"shape, {dt:.1f} s; {what}",
                "step_s": dt}
 
     steps_per_epoch = int(g.num_edges / (BATCH * 40))        # src/train_lightgcn.py:92
@@ -439,12 +509,12 @@ def main():
         "metric": "lgconv_gedges_per_s", "value": gedges, "unit": "GEdges/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: LightGCN K={layers} d={dim}, N={g.num_nodes}, nnz={nnz}, "
-                               f"batch={BATCH}, full training step (fwd+BPR+bwd+Adam)",
+        "config": {"workload": workload_name(args.config, g, dim, layers),
                    "l2": "inputs (>=1 GB of tables per step) exceed the 126 MB L2; no flush",
                    "steps_per_epoch": steps_per_epoch,
                    "parallelism": "single GPU" if world == 1 else par},
         "epoch_s": ms_step * steps_per_epoch * 1e-3,
+        "epoch_measured": epoch,
         "losses_last_step": last_losses,
         "e2e": {"value": e2e_gedges, "unit": "GEdges/s", "h2d_bytes_per_step": 3 * BATCH * 8,
                 "d2h_bytes_per_step": 12, "ms_per_step": e2e_s / args.steps * 1e3,
@@ -472,6 +542,51 @@ def finish(world, trainer):
         sys.stderr.flush()
         os._exit(0)
     return 0
+
+
+def bench_epoch(model, trainer, ei, ew, g, dev, dim):
+    """ONE epoch as the reference runs it (`TrainLightGCN.train`, src/train_lightgcn.py:79-121): n_batch =
+    int(E / (B * 40)) mini-batches drawn by the device sampler (`batch_loader`), each a fused step, then
+    the evaluation of `test()` (:155-162): top-20 of every evaluation user and recall@20 -- one timed
+    region (CUDA events around it; the only host reads are the epoch's mean losses and the two metrics)."""
+    import torch
+    from gnn_ecommerce_b200 import ops, scoring, synth
+    from gnn_ecommerce_b200.sampler import DeviceSampler
+    k = 20
+    held = synth.make_heldout(g, max(1000, g.n_users // 50))        # users with a held-out purchase (~2 %)
+    pl = synth.purchase_lists(g, held)
+    sampler = DeviceSampler.from_lists(pl.users, pl.pos_ptr, pl.pos_items, pl.ign_ptr, pl.ign_items,
+                                       g.n_users, g.n_items, dev, seed=7)
+    ptr, items = synth.seen_lists(g, held.users)
+    seen = scoring.SeenLists.from_numpy(ptr, items, dev)
+    eval_users = torch.from_numpy(held.users).to(dev)
+    held_ptr, held_items = torch.from_numpy(held.ptr).to(dev), torch.from_numpy(held.items).to(dev)
+    n_batch = int(g.num_edges / (BATCH * 40))
+
+    def run():
+        acc = torch.zeros(3, dtype=torch.float32, device=dev)
+        for _ in range(n_batch):
+            u, p, n = sampler.sample(BATCH)
+            acc += trainer.step(ei, ew, u, p, n, DECAY)
+        with torch.no_grad():
+            rows = ops.full_rows(model.cached_embedding(ei, ew))
+            top, _ = scoring.score_topk(rows[:g.n_users], rows[g.n_users:], eval_users, seen.ptr, seen.items, k, d=dim)
+            prec, rec, _ = scoring.mark_mapk(top, held_ptr, held_items)
+        return (acc / n_batch).cpu().tolist(), prec, rec
+
+    run()                                                           # warm-up epoch (allocations, schedules)
+    torch.cuda.synchronize()
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    beg.record()
+    losses, prec, rec = run()
+    end.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    return {"epoch_s": beg.elapsed_time(end) * 1e-3, "wall_s": wall, "n_batch": n_batch, "batch": BATCH,
+            "eval_users": int(held.users.size), "k": k, "mean_losses": losses, "precision_at_k": prec,
+            "recall_at_k": rec,
+            "what": "device sampler + n_batch fused steps + top-20 of the evaluation users + recall@20, one timed region"}
 
 
 def bench_scoring(rows, g, dev, args, pk, dim, world=1, rank=0):
@@ -522,6 +637,42 @@ def bench_scoring(rows, g, dev, args, pk, dim, world=1, rank=0):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # ---- end to end through the public call: pinned host user ids in, host top-k array out
+    host_users = torch.arange(u0, u1, dtype=torch.int64).pin_memory()
+    e2e_ms = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        uid = host_users.to(dev, non_blocking=True)
+        top_e, _ = scoring.score_topk(user_t, item_t, uid, seen.ptr, seen.items, k, d=dim)
+        host_top = scoring.topk_to_host(top_e)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e = float(np.median(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = float(t.item())
+    # ---- the timed result itself is checked: 512 sampled users against a plain fp32 torch product
+    # with the reference's multiplicative mask (src/lightgcn.py:173-177); ties within 2e-6 may swap
+    n_chk = min(512, u1 - u0)
+    chk = torch.from_numpy(np.random.default_rng(5).choice(u1 - u0, n_chk, replace=False)).to(dev)
+    with torch.no_grad():
+        old_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        pred = user_t[users[chk], :dim].double() @ item_t[:, :dim].double().t()
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        mask = torch.zeros_like(pred)
+        lo, hi = seen.ptr[chk], seen.ptr[chk + 1]
+        for i in range(n_chk):
+            mask[i, seen.items[int(lo[i]):int(hi[i])]] = 1.0
+        ref = pred * (1 - mask)
+        ref_kth = ref.topk(k, dim=-1).values[:, -1]
+        got_scores = torch.gather(ref, 1, top[chk])
+        tol = 2e-6 * ref.abs().amax(dim=-1)
+        bad = int(((got_scores.min(dim=-1).values + tol) < ref_kth).sum())
+        dup = int((torch.sort(top[chk], dim=-1).values.diff(dim=-1) == 0).any(dim=-1).sum())
+    check = {"users_checked": n_chk, "users_with_a_wrong_item": bad, "users_with_duplicates": dup,
+             "host_array_matches_device": bool((torch.from_numpy(host_top.astype(np.int64)).to(dev) == top_e).all())}
     flops_local = 2.0 * (u1 - u0) * g.n_items * dim
     flops = 2.0 * n_score * g.n_items * dim
     tf = flops / (ms * 1e-3) / 1e12
@@ -535,6 +686,10 @@ def bench_scoring(rows, g, dev, args, pk, dim, world=1, rank=0):
                          "peak_source": pk["source"], "kernel_ms": gemm_ms,
                          "whole_call_tflops": tf, "whole_call_frac": tf / (pk["bf16_tflops"] * world)},
             "class_ms": class_ms, "rep_ms": rep_ms,
+            "e2e": {"value": n_score / (e2e * 1e-3), "unit": "users/s", "ms": e2e, "rep_ms": e2e_ms,
+                    "h2d_bytes": int((u1 - u0) * 8), "d2h_bytes": int((u1 - u0) * k * 4),
+                    "what": "pinned host user ids -> device, top-k, int32 ids -> pinned host array"},
+            "check": check,
             "fallback_users": st[0], "candidate_groups": st[1]}
 
 

@@ -24,6 +24,14 @@ class GraphInfo(C.Structure):
                 ("w_hat", c_vp), ("deg", c_vp), ("dis", c_vp)]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [("has_plan", c_i32), ("sweep_slots_per_unit", c_i32), ("sweep_units", c_i64),
+                ("sweep_rows", c_i64), ("sweep_edges", c_i64), ("sweep_sources", c_i64),
+                ("sweep_pieces_split_rows", c_i64), ("sweep_partial_slots", c_i64),
+                ("sweep_iterations", c_i64), ("sweep_windows", c_i64),
+                ("rows_rows", c_i64), ("rows_edges", c_i64), ("rows_sources", c_i64)]
+
+
 class TrainStepArgs(C.Structure):
     _fields_ = [("ld", c_i32), ("num_layers", c_i32), ("h_alpha", C.POINTER(c_f32)),
                 ("batch", c_i64), ("users", c_vp), ("pos", c_vp), ("neg", c_vp),
@@ -60,6 +68,7 @@ _SIGNATURES = {
     "lgc_graph_build_rect": (C.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
     "lgc_graph_destroy": (C.c_int, [c_vp]),
     "lgc_graph_get_info": (C.c_int, [c_vp, C.POINTER(GraphInfo)]),
+    "lgc_graph_plan_info": (C.c_int, [c_vp, C.c_int, C.POINTER(PlanInfo)]),
     "lgc_spmm_workspace_bytes": (c_sz, [c_vp, C.c_int]),
     "lgc_spmm": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgc_spmm_ex": (C.c_int, [c_vp, C.c_int, c_vp, C.POINTER(SpmmEpilogue), c_vp, c_sz, c_vp]),

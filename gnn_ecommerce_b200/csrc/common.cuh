@@ -61,7 +61,28 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_record(tag, st, false); }
 };
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (grid sizing of the small helper kernels)
+constexpr int kMaxDevices = 64;
+
+// Device of the calling thread, clamped into [0, kMaxDevices): index of the per-device caches of
+// function attributes / occupancy (cudaFuncSetAttribute is per device; a process may use several).
+static inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
+// SM count of the current device (cached per device)
+static inline int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int slot = current_device_slot();
+  if (!sms[slot]) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    sms[slot] = n;
+  }
+  return sms[slot];
+}
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

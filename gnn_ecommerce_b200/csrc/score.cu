@@ -1216,7 +1216,8 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
                      (uintptr_t)a->item_emb % 16 == 0;
   LGC_REQUIRE(f4_ok, "embedding rows must be 16-byte aligned (ld % 4 == 0)");
 
-  static bool attr_done = false;
+  static bool attr_done_dev[kMaxDevices] = {};       // cudaFuncSetAttribute is per device
+  bool& attr_done = attr_done_dev[current_device_slot()];
   if (!attr_done) {
     LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     LGC_CUDA(cudaFuncSetAttribute(k_score_gemm<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -854,7 +854,8 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   // ---- ... else the chunked heavy-row kernel (+ the sums of split rows): launched first so that
   // their CTAs find room
   if (!sw && g->num_chunks > 0) {
-    static int occ_heavy = 0;            // per instantiation: resident CTAs per SM
+    static int occ_heavy_dev[kMaxDevices] = {};   // per instantiation and device: resident CTAs per SM
+    int& occ_heavy = occ_heavy_dev[current_device_slot()];
     if (!occ_heavy) {
       LGC_CUDA(cudaFuncSetAttribute(k_spmm_heavy<L, V, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)HC::SMEM));
@@ -864,7 +865,7 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
       occ_heavy = occ > 0 ? occ : 1;
     }
     const int per_sm = ov ? std::min(occ_heavy, kHeavyCtasOverlap) : occ_heavy;
-    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, kHeavyWarps), (int64_t)kNumSMs * per_sm);
+    const int grid_heavy = (int)std::min<int64_t>(ceil_div(g->num_chunks, kHeavyWarps), (int64_t)device_sm_count() * per_sm);
     {
       ProfScope ps(PROF_HEAVY + (MODE & 3), hs);
       k_spmm_heavy<L, V, MODE><<<grid_heavy, 32 * kHeavyWarps, HC::SMEM, hs>>>(
@@ -886,8 +887,11 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
   if (sw && sweep_row_plan(sw)) return launch_rows(g, sweep_row_plan(sw), HC::LD, x, (EpiMode)MODE, a, st);
   // ---- ... or the round-1 light-row kernel (rows up to light_max_degree)
   {
-    static int occ_light[kMaxHist + 1] = {};   // per instantiation and buffer count: resident CTAs per SM
-    static size_t smem_set = 0;
+    // per instantiation, device and buffer count: resident CTAs per SM; largest shared-memory size set
+    static int occ_light_dev[kMaxDevices][kMaxHist + 1] = {};
+    static size_t smem_set_dev[kMaxDevices] = {};
+    int* const occ_light = occ_light_dev[current_device_slot()];
+    size_t& smem_set = smem_set_dev[current_device_slot()];
     if (smem > smem_set) {
       LGC_CUDA(cudaFuncSetAttribute(k_spmm_light<LL, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
@@ -900,7 +904,7 @@ int launch_lv(const lgc_graph* g, const float* x, const EpiArgs& a, float* parti
     }
     const int per_sm = ov ? std::min(occ_light[nbuf], light_cap) : occ_light[nbuf];
     const int n_tiles = (int)ceil_div(n, LC::TR);
-    const int grid = (int)std::min<int64_t>((int64_t)kNumSMs * per_sm, ceil_div(n_tiles, warps));
+    const int grid = (int)std::min<int64_t>((int64_t)device_sm_count() * per_sm, ceil_div(n_tiles, warps));
     ProfScope ps(PROF_LIGHT + (MODE & 3), st);
     k_spmm_light<LL, LV, MODE><<<grid, 32 * warps, smem, st>>>(g->rowptr, g->src, g->w_hat, x, (int)n,
                                                                 g->light_max_degree, light_phase_buffer(), a);
@@ -971,6 +975,15 @@ extern "C" int lgc_ld_supported(int ld) {
   for (auto& p : ok)
     if (p[0] == rs.L && p[1] == rs.V) return 1;
   return 0;
+}
+
+extern "C" int lgc_graph_plan_info(const lgc_graph_t* g, int ld, lgc_plan_info* info) {
+  LGC_REQUIRE(g && info, "null argument");
+  *info = lgc_plan_info{};
+  const SweepSched* sw = (g->num_chunks > 0 || rows_kernel_enabled()) ? sweep_get(g, ld) : nullptr;
+  if (sw) sweep_info(sw, info);
+  info->has_plan = sw ? 1 : 0;
+  return LGC_OK;
 }
 
 extern "C" size_t lgc_spmm_workspace_bytes(const lgc_graph_t* g, int ld) {

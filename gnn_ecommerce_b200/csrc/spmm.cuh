@@ -109,6 +109,7 @@ struct RowPlan {
   int2* rec = nullptr;
 };
 const RowPlan* sweep_row_plan(const SweepSched* s);
+void sweep_info(const SweepSched* s, lgc_plan_info* info);
 bool rows_kernel_enabled();
 int launch_rows(const lgc_graph* g, const RowPlan* plan, int ld, const float* x, EpiMode mode, const EpiArgs& args,
                 cudaStream_t st);

@@ -58,6 +58,8 @@ struct SweepSched {
   int64_t n_rows = 0, n_edges = 0, n_iters = 0;
   int64_t n_split_rows = 0, n_partial_slots = 0;
   int window_span = 1, n_windows = 0;   // source rows per window; windows over the gathered table
+  // bookkeeping for the roofline accounting (lgc_graph_plan_info)
+  int64_t rows_rows = 0, rows_edges = 0, rows_sources = 0, sweep_sources = 0;
   int32_t* warp_ptr = nullptr;   // [n_warps + 1] first iteration of every warp (32 records each)
   int2* rec = nullptr;           // [n_iters * 32] {source | slot << src_bits, weight bits}
   int2* unit_rows = nullptr;     // [n_units * S] {row, partial slot or -1}; row < 0: unused
@@ -142,6 +144,22 @@ __global__ void k_sweep_fill(int64_t n_records, int n_warps, const int32_t* __re
     if (last) r.x |= (int)0x80000000u;
   }
   rec[t] = r;
+}
+
+// bitmap of the source rows gathered by the rows of one class (in_sweep == which), one warp per row
+__global__ void k_mark_sources(int64_t n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                               const uint8_t* __restrict__ in_sweep, int which, uint32_t* __restrict__ bits) {
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows || in_sweep[r] != which) return;
+  for (int j = rowptr[r] + lane; j < rowptr[r + 1]; j += 32) atomicOr(&bits[src[j] >> 5], 1u << (src[j] & 31));
+}
+__global__ void k_popcount(int64_t n_words, const uint32_t* __restrict__ bits, unsigned long long* __restrict__ out) {
+  unsigned long long c = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x)
+    c += __popc(bits[i]);
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // (source, weight) of every CSR entry side by side: the rows kernel reads a row's edges as one
@@ -345,9 +363,30 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
       SWEEP_CUDA(cudaGetLastError());
     }
   }
+  // ---- distinct gathered source rows per kernel class (algorithmic bytes of a launch)
+  unsigned long long h_distinct[2] = {0, 0};
+  {
+    std::vector<uint8_t> in_sweep((size_t)n, 0);
+    for (int32_t r : rows) in_sweep[r] = 1;
+    Dev<uint8_t> d_in;
+    Dev<uint32_t> d_bits;
+    Dev<unsigned long long> d_cnt2;
+    const int64_t n_words = (g->num_cols + 31) / 32;
+    SWEEP_CUDA(d_in.upload(in_sweep)); SWEEP_CUDA(d_bits.alloc(n_words)); SWEEP_CUDA(d_cnt2.alloc(2));
+    SWEEP_CUDA(cudaMemset(d_cnt2.p, 0, 16));
+    for (int which = 0; which < 2; ++which) {
+      SWEEP_CUDA(cudaMemset(d_bits.p, 0, n_words * 4));
+      k_mark_sources<<<(int)ceil_div(n * 32, threads), threads>>>(n, g->rowptr, g->src, d_in.p, which, d_bits.p);
+      k_popcount<<<148 * 4, threads>>>(n_words, d_bits.p, d_cnt2.p + which);
+      SWEEP_CUDA(cudaGetLastError());
+    }
+    SWEEP_CUDA(cudaMemcpy(h_distinct, d_cnt2.p, 16, cudaMemcpyDeviceToHost));
+  }
   SWEEP_CUDA(cudaDeviceSynchronize());
 
   SweepSched* s = new SweepSched();
+  s->rows_rows = n - (int64_t)rows.size(); s->rows_edges = g->nnz - n_edges;
+  s->rows_sources = (int64_t)h_distinct[0]; s->sweep_sources = (int64_t)h_distinct[1];
   s->plan.n_blocks = n_blocks; s->plan.num_rows = n;
   s->plan.perm = d_perm.release(); s->plan.blk_cnt = d_cnt.release(); s->plan.rec = d_rec2.release();
   s->slots = S; s->src_bits = src_bits;
@@ -555,6 +594,15 @@ const SweepSched* sweep_get(const lgc_graph* g, int ld) {
   }
   if (g->n_sweep_failed < kMaxSweepScheds) g->sweep_failed[g->n_sweep_failed++] = S;
   return nullptr;
+}
+
+void sweep_info(const SweepSched* s, lgc_plan_info* info) {
+  info->sweep_rows = s->n_rows; info->sweep_edges = s->n_edges; info->sweep_sources = s->sweep_sources;
+  info->sweep_pieces_split_rows = s->n_split_rows; info->sweep_partial_slots = s->n_partial_slots;
+  info->sweep_slots_per_unit = s->slots; info->sweep_units = s->n_units; info->sweep_iterations = s->n_iters;
+  info->sweep_windows = s->n_windows;
+  info->rows_rows = s->plan.perm ? s->rows_rows : 0; info->rows_edges = s->plan.perm ? s->rows_edges : 0;
+  info->rows_sources = s->plan.perm ? s->rows_sources : 0;
 }
 
 int launch_sweep(const lgc_graph* g, const SweepSched* s, int ld, const float* x, EpiMode mode, const EpiArgs& a,

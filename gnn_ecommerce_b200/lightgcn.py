@@ -147,6 +147,23 @@ class LightGCN(torch.nn.Module):
             items = dst_index[items.view(-1)].view(*items.size())
         return items
 
+    def recommendK_array(self, edge_index, edge_weight, n_users, n_items, interactions_t, user_id_list,
+                         k: int = 5, to_host: bool = True):
+        """`recommendK` without the pandas packaging: the top-k item ids as one `[len(user_id_list), k]`
+        array -- a host ndarray (int32, through pinned memory) or, with `to_host=False`, the int64 device
+        tensor. `user_id_list` may be a list, an ndarray or a tensor (pinned host tensors are copied
+        asynchronously)."""
+        embeds = self.cached_embedding(edge_index, edge_weight)
+        if isinstance(user_id_list, Tensor):
+            users = user_id_list.to(device=embeds.device, dtype=torch.int64, non_blocking=True)
+        else:
+            users = torch.as_tensor(np.asarray(user_id_list, dtype=np.int64), device=embeds.device)
+        seen = scoring.as_seen_lists(interactions_t, users.numel(), n_items, embeds.device)
+        rows = ops.full_rows(embeds)
+        items, _ = scoring.score_topk(rows[:n_users], rows[n_users:n_users + n_items], users,
+                                      seen.ptr, seen.items, k, d=self.embedding_dim)
+        return scoring.topk_to_host(items) if to_host else items
+
     def recommendK(self, edge_index, edge_weight, n_users, n_items, interactions_t, user_id_list,
                    k: int = 5):
         """Top-k unseen-first item lists for `user_id_list` (reference `src/lightgcn.py:169-182`).
@@ -155,14 +172,8 @@ class LightGCN(torch.nn.Module):
         device) or a `scoring.SeenLists` CSR; masking is multiplicative like the reference's
         (`pred * (1 - mask)`: a seen item scores 0.0). Returns the same two-column frame
         (`user_ID`, `top_rlvnt_itm`)."""
-        embeds = self.cached_embedding(edge_index, edge_weight)
-        seen = scoring.as_seen_lists(interactions_t, len(user_id_list), n_items, embeds.device)
-        users = torch.as_tensor(np.asarray(user_id_list, dtype=np.int64), device=embeds.device)
-        rows = ops.full_rows(embeds)
-        items, _ = scoring.score_topk(rows[:n_users], rows[n_users:n_users + n_items], users,
-                                      seen.ptr, seen.items, k, d=self.embedding_dim)
-        top_index_df = pd.DataFrame({'user_ID': list(user_id_list),
-                                     'top_rlvnt_itm': items.cpu().numpy().tolist()})
+        top = self.recommendK_array(edge_index, edge_weight, n_users, n_items, interactions_t, user_id_list, k)
+        top_index_df = pd.DataFrame({'user_ID': list(user_id_list), 'top_rlvnt_itm': top.tolist()})
         return top_index_df[['user_ID', 'top_rlvnt_itm']]
 
     def MARK_MAPK(self, test_pos_list_df, top_index_df, k):

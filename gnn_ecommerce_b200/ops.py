@@ -6,6 +6,7 @@ Everything here is plumbing (device memory, streams, autograd glue); the arithme
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -45,19 +46,29 @@ def pad_table(x: Tensor) -> Tensor:
     return out
 
 
-_PADDED_STORAGES = set()   # storage pointers handed out by `new_table` (pad columns are zero)
+# storage pointer -> weak reference to the zero-initialised base tensor `new_table` handed out. A
+# view keeps its base alive (`._base`), so the entry lives exactly as long as some view of the
+# table does; once the table is freed the entry disappears with it and a later allocation that
+# reuses the address is NOT mistaken for a zero-padded table.
+_PADDED_TABLES = {}
 
 
 def _pad_is_zero_view(x: Tensor, ld: int) -> bool:
-    return x.untyped_storage().data_ptr() in _PADDED_STORAGES
+    ptr = x.untyped_storage().data_ptr()
+    ref = _PADDED_TABLES.get(ptr)
+    base = ref() if ref is not None else None
+    return base is not None and base.untyped_storage().data_ptr() == ptr and base.stride(0) == ld
 
 
 def new_table(n_rows: int, d: int, device) -> Tensor:
     """Zeroed [n_rows, d] view of a padded [n_rows, ld] allocation."""
     ld = padded_dim(d)
     store = torch.zeros(n_rows, ld, dtype=torch.float32, device=device)
-    _PADDED_STORAGES.add(store.untyped_storage().data_ptr())
-    return store[:, :d] if ld != d else store
+    if ld == d:
+        return store
+    ptr = store.untyped_storage().data_ptr()
+    _PADDED_TABLES[ptr] = weakref.ref(store, lambda _r, _p=ptr: _PADDED_TABLES.pop(_p, None))
+    return store[:, :d]
 
 
 def full_rows(x: Tensor) -> Tensor:

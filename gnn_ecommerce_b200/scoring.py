@@ -107,6 +107,26 @@ def score_topk(user_emb: Tensor, item_emb: Tensor, user_ids: Optional[Tensor],
     return (items, scores, stats) if return_stats else (items, scores)
 
 
+_PINNED = {}
+
+
+def topk_to_host(items: Tensor, dtype=torch.int32) -> np.ndarray:
+    """Top-k item ids [U, k] -> host ndarray through a cached pinned buffer (one asynchronous D2H copy
+    + one synchronisation). int32 by default: item ids fit, and the copy is what an all-user call is
+    bound by on the host side (1.6 M x 20 ids = 128 MB). The reference does
+    `.cpu().numpy().tolist()` on a [U, n_items] score matrix instead (src/lightgcn.py:170-177)."""
+    dev_items = items.to(dtype) if items.dtype != dtype else items
+    key = (dtype, items.device.index)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < dev_items.numel():
+        buf = torch.empty(max(dev_items.numel(), 1), dtype=dtype).pin_memory()
+        _PINNED[key] = buf
+    host = buf[:dev_items.numel()].view(dev_items.shape)
+    host.copy_(dev_items, non_blocking=True)
+    torch.cuda.current_stream(items.device).synchronize()
+    return host.numpy()
+
+
 def mark_mapk(topk_items: Tensor, held_ptr: Tensor, held_items: Tensor):
     """Device-side `MARK_MAPK` (reference `src/lightgcn.py:184-189`): returns
     `(mean precision@k, mean recall@k, per_user [U, 2])` for top-k lists already on the device

@@ -91,16 +91,18 @@ class FusedBPRTrainer:
         ws = self._workspace(g, ld, k, batch)
         alpha = model.alpha_host()
         loss3 = torch.empty(3, dtype=torch.float32, device=rows.device)
-        self.step_count += 1
         args = _capi.TrainStepArgs(
             ld=ld, num_layers=k, h_alpha=(C.c_float * len(alpha))(*alpha), batch=batch,
             users=_ptr(users), pos=_ptr(pos), neg=_ptr(neg), decay=float(decay), lr=self.lr,
-            beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, step=self.step_count,
+            beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, step=self.step_count + 1,
             e0=_ptr(rows), m=_ptr(self.m), v=_ptr(self.v), loss3=_ptr(loss3),
             workspace=_ptr(ws), workspace_bytes=ws.numel())
         with torch.cuda.device(rows.device):
             rc = self._lib.lgc_train_step(g.handle, C.byref(args), _stream())
+        if rc != 0:
+            self._ws_key = None          # a failed step may leave gradient rows behind: re-zero the workspace next time
         _capi.check(rc, "lgc_train_step")
+        self.step_count += 1             # only a completed step advances the Adam bias correction
         model._weights_epoch = getattr(model, "_weights_epoch", 0) + 1     # invalidates cached_embedding
         return loss3
 

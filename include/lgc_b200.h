@@ -112,6 +112,22 @@ typedef struct {
 } lgc_graph_info;
 int lgc_graph_get_info(const lgc_graph_t* graph, lgc_graph_info* info);
 
+/* How the SpMM (the LGConv operator, src/lightgcn.py:96) splits the rows of this graph for row width
+ * `ld` (built on the first query for that width): the high-degree rows go to the sweep kernel
+ * (output rows pinned in shared memory, all CTAs walk the source table window by window), the rest
+ * to the rows kernel (one sub-warp per row). `*_sources` = distinct source rows the class gathers
+ * -- with the edge and row counts, the algorithmic bytes of one launch (bench.py). has_plan == 0:
+ * no schedule for this width (ld % 16 != 0, or >= 2^25 source rows): the round-1 chunked kernels run. */
+typedef struct {
+  int32_t has_plan;
+  int32_t sweep_slots_per_unit;
+  int64_t sweep_units;
+  int64_t sweep_rows, sweep_edges, sweep_sources;
+  int64_t sweep_pieces_split_rows, sweep_partial_slots, sweep_iterations, sweep_windows;
+  int64_t rows_rows, rows_edges, rows_sources;
+} lgc_plan_info;
+int lgc_graph_plan_info(const lgc_graph_t* graph, int ld, lgc_plan_info* info);
+
 /* ------------------------------------------------------------------ LGConv (src/lightgcn.py:96)
  * y = A_hat x. x, y: [num_nodes, ld]; must not alias. Workspace holds the partial rows of the
  * hub rows that are split over several warps (usually a few MB; may be 0 bytes). */
