@@ -9,7 +9,7 @@ library has not been built.
 from . import synth  # noqa: F401  (numpy only)
 
 __all__ = ["LightGCN", "LGConv", "BPRLoss", "FusedBPRTrainer", "SeenLists", "score_topk", "synth",
-           "DeviceSampler", "save_model", "load_model", "make_sharded_trainer"]
+           "DeviceSampler", "save_model", "load_model", "make_sharded_trainer", "LightGCNService"]
 
 
 def __getattr__(name):
@@ -28,6 +28,9 @@ def __getattr__(name):
     if name in ("save_model", "load_model"):
         from . import checkpoint
         return getattr(checkpoint, name)
+    if name == "LightGCNService":
+        from .serving import LightGCNService
+        return LightGCNService
     if name == "make_sharded_trainer":
         from .sharded import make_sharded_trainer
         return make_sharded_trainer
