@@ -44,7 +44,8 @@ class SpmmEpilogue(C.Structure):
     _fields_ = [("mode", c_i32), ("a0", c_f32), ("a1", c_f32), ("scale", c_f32), ("beta", c_f32),
                 ("y", c_vp), ("acc", c_vp), ("xrow", c_vp), ("addend", c_vp), ("p", c_vp), ("m", c_vp),
                 ("v", c_vp), ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("eps", c_f64),
-                ("step", c_i64), ("adam_scalars", c_vp)]
+                ("step", c_i64), ("adam_scalars", c_vp), ("hist", c_vp * 6), ("ah", c_f32 * 6),
+                ("n_hist", c_i32)]
 
 
 class ScoreTopkArgs(C.Structure):
@@ -72,6 +73,7 @@ _SIGNATURES = {
     "lgc_spmm_workspace_bytes": (c_sz, [c_vp, C.c_int]),
     "lgc_spmm": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgc_spmm_ex": (C.c_int, [c_vp, C.c_int, c_vp, C.POINTER(SpmmEpilogue), c_vp, c_sz, c_vp]),
+    "lgc_epilogue_apply": (C.c_int, [c_i64, C.c_int, c_vp, C.POINTER(SpmmEpilogue), c_vp]),
     "lgc_propagate_workspace_bytes": (c_sz, [c_vp, C.c_int, C.c_int]),
     "lgc_propagate": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_f32), c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgc_pair_scores": (C.c_int, [C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),

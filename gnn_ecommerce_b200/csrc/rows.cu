@@ -201,6 +201,7 @@ int launch_rows_lv(const RowPlan* p, const float* x, EpiMode mode, const EpiArgs
 int launch_rows(const lgc_graph* g, const RowPlan* plan, int ld, const float* x, EpiMode mode, const EpiArgs& a,
                 cudaStream_t st) {
   if (!g || !plan) return LGC_ERR_INVALID;
+  if (plan->n_active == 0) return LGC_OK;              // every row went to the sweep
   int rc = LGC_ERR_UNSUPPORTED;
   // sub-warp geometry per row width: L lanes x V float4 (few lanes per row: more rows per warp instruction)
 #define LGC_ROWS_CASE(LDV, LL, LV) case LDV: rc = launch_rows_lv<LL, LV>(plan, x, mode, a, g->rowptr, st); break;

@@ -1003,14 +1003,7 @@ extern "C" int lgc_spmm(const lgc_graph_t* g, int ld, const float* x, float* y, 
   return launch_spmm(g, ld, x, EPI_PLAIN, a, (float*)workspace, (cudaStream_t)stream);
 }
 
-extern "C" int lgc_spmm_ex(const lgc_graph_t* g, int ld, const float* x, const lgc_spmm_epilogue* e,
-                           void* workspace, size_t workspace_bytes, void* stream) {
-  LGC_REQUIRE(g && x && e, "null argument");
-  if (workspace_bytes < lgc_spmm_workspace_bytes(g, ld)) {
-    set_error("lgc_spmm_ex: workspace too small");
-    return LGC_ERR_WORKSPACE;
-  }
-  EpiArgs a;
+static int epilogue_args(const lgc_spmm_epilogue* e, const float* x, EpiArgs& a) {
   a.y = e->y; a.acc = e->acc; a.xrow = e->xrow; a.addend = e->addend;
   a.a0 = e->a0; a.a1 = e->a1; a.scale = e->scale; a.beta = e->beta;
   a.p = e->p; a.m = e->m; a.v = e->v;
@@ -1024,9 +1017,64 @@ extern "C" int lgc_spmm_ex(const lgc_graph_t* g, int ld, const float* x, const l
       if (e->adam_scalars) a.adam_dev = reinterpret_cast<const AdamScalars*>(e->adam_scalars);
       else a.adam = make_adam_scalars(e->lr, e->beta1, e->beta2, e->eps, e->step);
       break;
+    case LGC_EPI_FWD_FINAL:
+      LGC_REQUIRE(e->acc && e->n_hist >= 1 && e->n_hist <= kMaxHist, "FWD_FINAL needs acc and 1..6 layer tables");
+      a.n_hist = e->n_hist;
+      for (int i = 0; i < e->n_hist; ++i) {
+        LGC_REQUIRE(e->hist[i], "FWD_FINAL: null layer table");
+        a.hist[i] = e->hist[i];
+        a.ah[i] = e->ah[i];
+      }
+      break;
     default: LGC_REQUIRE(false, "unknown epilogue mode");
   }
+  return LGC_OK;
+}
+
+extern "C" int lgc_spmm_ex(const lgc_graph_t* g, int ld, const float* x, const lgc_spmm_epilogue* e,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  LGC_REQUIRE(g && x && e, "null argument");
+  if (workspace_bytes < lgc_spmm_workspace_bytes(g, ld)) {
+    set_error("lgc_spmm_ex: workspace too small");
+    return LGC_ERR_WORKSPACE;
+  }
+  EpiArgs a;
+  int rc = epilogue_args(e, x, a);
+  if (rc) return rc;
   return launch_spmm(g, ld, x, (EpiMode)e->mode, a, (float*)workspace, (cudaStream_t)stream);
+}
+
+namespace lgc {
+namespace {
+// the fused epilogue on existing row sums: one thread per float4 column of a row
+template <int MODE>
+__global__ void k_epilogue_apply(int64_t n_vec, const float* __restrict__ sums, EpiArgs args) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x)
+    epilogue<MODE>(args, (size_t)i * 4, ld_f4(sums + i * 4));
+}
+}  // namespace
+}  // namespace lgc
+
+extern "C" int lgc_epilogue_apply(int64_t n_rows, int ld, const float* sums, const lgc_spmm_epilogue* e,
+                                  void* stream) {
+  LGC_REQUIRE(sums && e && n_rows >= 0 && ld > 0 && ld % 4 == 0, "bad argument");
+  EpiArgs a;
+  int rc = epilogue_args(e, nullptr, a);
+  if (rc) return rc;
+  const int64_t n_vec = n_rows * (ld / 4);
+  if (n_vec == 0) return LGC_OK;
+  const int grid = (int)std::min<int64_t>(ceil_div(n_vec, 256), (int64_t)device_sm_count() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (e->mode) {
+    case LGC_EPI_PLAIN: k_epilogue_apply<EPI_PLAIN><<<grid, 256, 0, st>>>(n_vec, sums, a); break;
+    case LGC_EPI_FWD_INIT: k_epilogue_apply<EPI_FWD_INIT><<<grid, 256, 0, st>>>(n_vec, sums, a); break;
+    case LGC_EPI_FWD_RMW: k_epilogue_apply<EPI_FWD_RMW><<<grid, 256, 0, st>>>(n_vec, sums, a); break;
+    case LGC_EPI_ADAM: k_epilogue_apply<EPI_ADAM><<<grid, 256, 0, st>>>(n_vec, sums, a); break;
+    case LGC_EPI_FWD_FINAL: k_epilogue_apply<EPI_FWD_FINAL><<<grid, 256, 0, st>>>(n_vec, sums, a); break;
+    default: break;
+  }
+  LGC_LAUNCH_CHECK();
+  return LGC_OK;
 }
 
 // Forward chain shared by lgc_propagate and lgc_train_step: layers 1..K-1 store x_l = A x_{l-1}

@@ -103,7 +103,7 @@ bool sweep_has_rows(const SweepSched* s);          // false: no row qualified, n
 // light-row kernel instead (no plan).
 constexpr int kRowsBlock = 256;
 struct RowPlan {
-  int64_t n_blocks = 0, num_rows = 0;
+  int64_t n_blocks = 0, num_rows = 0, n_active = 0;   // n_active: rows the plan holds (0: nothing to launch)
   uint8_t* perm = nullptr;
   int32_t* blk_cnt = nullptr;
   int2* rec = nullptr;

@@ -209,7 +209,11 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   // (LGC_ROWS=0) every row above its limit must fit.
   const bool with_plan = rows_kernel_enabled();
   static const int rows_max_degree = [] { const char* e = getenv("LGC_ROWS_MAX_DEGREE"); int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
-  const int threshold = with_plan ? rows_max_degree : g->light_max_degree;
+  // A rectangular operator whose rows all fit (the item-partial operator of the multi-GPU step: every
+  // item row, few edges each per rank) goes to the sweep entirely: one launch instead of two, and the
+  // rows with few LOCAL edges still share the window of the source table with the hubs.
+  const bool all_rows = with_plan && g->num_cols != g->num_nodes && n <= (int64_t)n_units * S * 8 / 10;
+  const int threshold = all_rows ? -1 : (with_plan ? rows_max_degree : g->light_max_degree);
   std::vector<int32_t> rows;
   for (int64_t r = 0; r < n; ++r)
     if (rp[r + 1] - rp[r] > threshold) rows.push_back((int32_t)r);
@@ -387,7 +391,7 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   SweepSched* s = new SweepSched();
   s->rows_rows = n - (int64_t)rows.size(); s->rows_edges = g->nnz - n_edges;
   s->rows_sources = (int64_t)h_distinct[0]; s->sweep_sources = (int64_t)h_distinct[1];
-  s->plan.n_blocks = n_blocks; s->plan.num_rows = n;
+  s->plan.n_blocks = n_blocks; s->plan.num_rows = n; s->plan.n_active = n - (int64_t)rows.size();
   s->plan.perm = d_perm.release(); s->plan.blk_cnt = d_cnt.release(); s->plan.rec = d_rec2.release();
   s->slots = S; s->src_bits = src_bits;
   s->n_ctas = n_sms; s->n_warps = n_warps; s->n_units = n_units;

@@ -113,17 +113,49 @@ class CudaBackend:
     def workspace(self, handle, ld: int, device) -> Tensor:
         return torch.empty(max(256, self._lib.lgc_spmm_workspace_bytes(handle, ld)), dtype=torch.uint8, device=device)
 
-    def spmm_ex(self, handle, ld: int, x: Tensor, ws: Tensor, mode: int, *, y=None, acc=None, xrow=None,
-                addend=None, a0=0.0, a1=0.0, scale=1.0, beta=0.0, p=None, m=None, v=None, lr=0.0,
-                betas=(0.9, 0.999), eps=1e-8, step=1, adam_scalars=None) -> None:
-        from .graph import _ptr, _stream
+    def _epilogue(self, mode, y, acc, xrow, addend, a0, a1, scale, beta, p, m, v, lr, betas, eps, step,
+                  adam_scalars, hist, ah):
+        from .graph import _ptr
         e = self._capi.SpmmEpilogue(mode=mode, a0=a0, a1=a1, scale=scale, beta=beta, y=_ptr(y), acc=_ptr(acc),
                                     xrow=_ptr(xrow), addend=_ptr(addend), p=_ptr(p), m=_ptr(m), v=_ptr(v),
                                     lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, step=step,
                                     adam_scalars=_ptr(adam_scalars))
+        if hist is not None:
+            e.n_hist = len(hist)
+            for i, (t, w) in enumerate(zip(hist, ah)):
+                e.hist[i] = _ptr(t)
+                e.ah[i] = float(w)
+        return e
+
+    def spmm_ex(self, handle, ld: int, x: Tensor, ws: Tensor, mode: int, *, y=None, acc=None, xrow=None,
+                addend=None, a0=0.0, a1=0.0, scale=1.0, beta=0.0, p=None, m=None, v=None, lr=0.0,
+                betas=(0.9, 0.999), eps=1e-8, step=1, adam_scalars=None, hist=None, ah=None) -> None:
+        """One LGConv layer with a fused epilogue (mode: 0 PLAIN, 1 FWD_INIT, 2 FWD_RMW, 3 ADAM, 4 FWD_FINAL)."""
+        from .graph import _ptr, _stream
+        e = self._epilogue(mode, y, acc, xrow, addend, a0, a1, scale, beta, p, m, v, lr, betas, eps, step,
+                           adam_scalars, hist, ah)
         with torch.cuda.device(x.device):
             rc = self._lib.lgc_spmm_ex(handle, ld, _ptr(x), C.byref(e), _ptr(ws), ws.numel(), _stream())
         self._capi.check(rc, "lgc_spmm_ex")
+
+    def epilogue_apply(self, sums: Tensor, ld: int, mode: int, *, y=None, acc=None, xrow=None, addend=None, a0=0.0,
+                       a1=0.0, scale=1.0, beta=0.0, p=None, m=None, v=None, lr=0.0, betas=(0.9, 0.999), eps=1e-8,
+                       step=1, adam_scalars=None, hist=None, ah=None) -> None:
+        """The same epilogue on row sums that already exist (the all-reduced item rows)."""
+        from .graph import _ptr, _stream
+        e = self._epilogue(mode, y, acc, xrow, addend, a0, a1, scale, beta, p, m, v, lr, betas, eps, step,
+                           adam_scalars, hist, ah)
+        with torch.cuda.device(sums.device):
+            rc = self._lib.lgc_epilogue_apply(sums.size(0), ld, _ptr(sums), C.byref(e), _stream())
+        self._capi.check(rc, "lgc_epilogue_apply")
+
+    def row_degree(self, handle, n_rows: int, device) -> Tensor:
+        """fp32 weighted in-degree of every row of a rect graph, summed in edge-list order (bit-exact
+        to the CPU scatter_add_ of gcn_norm for the edges the graph holds)."""
+        from .graph import _from_device_ptr
+        info = self._capi.GraphInfo()
+        self._capi.check(self._lib.lgc_graph_get_info(handle, C.byref(info)), "lgc_graph_get_info")
+        return _from_device_ptr(info.deg, int(info.num_nodes), torch.float32, device)[:n_rows].clone()
 
     def scatter_add(self, table: Tensor, idx: Tensor, rows: Tensor) -> None:
         """table[idx[j]] += rows[j], duplicates in input order (deterministic); idx < 0 skipped."""
@@ -367,23 +399,69 @@ class BipartiteShardedTrainer(_GraphedStep):
     """Bipartite-aware sharding of the same step (~30x less traffic than the
     all-gather of whole tables): USERS are partitioned over the ranks (balanced by in-degree + 4),
     the small ITEM table is replicated. Per layer a rank computes its users' rows from the replicated
-    item table (fused epilogue, no communication) and the PARTIAL sums of every item row over its
-    own users; one all-reduce of the `[n_items, ld]` partials completes the item rows, whose
-    (tiny, replicated) epilogue every rank applies identically. Item-row sums are therefore reduced
-    in a different order than on one GPU: equal within fp32 tolerance, not bit-exact."""
+    item table (rows kernel, fused epilogue, no communication) and the PARTIAL sums of every item row
+    over its own users (sweep kernel); one all-reduce of the `[n_items, ld]` partials completes the
+    item rows, whose (replicated) epilogue is ONE launch of the same fused epilogue
+    (`lgc_epilogue_apply`). The all-reduce of layer l runs on NCCL's stream while the rank computes its
+    user rows of layer l and the item partials of layer l + 1. Item-row sums are reduced in a
+    different order than on one GPU: equal within fp32 tolerance, not bit-exact.
+
+    A rank needs only ITS OWN users' interactions: the two rectangular operators are built from that
+    slice (`from_pairs`), the item degrees are the all-reduced partial degrees, so no process ever
+    holds the global edge list (c5: 200 M interactions)."""
 
     def __init__(self, edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int, embedding_dim: int,
                  num_layers: int, init_weight: Tensor, n_users: int, lr: float = 0.005, betas=(0.9, 0.999),
                  eps: float = 1e-8, alpha: Optional[Sequence[float]] = None, group=None, backend=None,
                  ld: Optional[int] = None):
+        """From the reference's global edge list (`df_to_graph` layout: [[u; i], [i; u]], every rank passes
+        the same one): the first half holds every interaction once, in frame order."""
+        n_users = int(n_users)
+        assert int(edge_index[1].min().item()) >= 0
+        if not self._pairs_layout_ok(edge_index, n_users):
+            raise RuntimeError("the sharded step needs a symmetric graph (backward reuses the operator)")
+        e = edge_index.size(1) // 2
+        user, item = edge_index[0, :e], edge_index[1, :e] - n_users
+        w = edge_weight[:e] if edge_weight is not None else torch.ones(e, dtype=torch.float32, device=edge_index.device)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        deg_cnt = torch.bincount(user, minlength=n_users)
+        part = RowPartition(deg_cnt.cpu().numpy(), world)
+        lo, hi = part.lo(rank), part.hi(rank)
+        mine = (user >= lo) & (user < hi)                                    # keeps frame order
+        self._setup(user[mine], item[mine], w[mine].float(), part, n_users, int(num_nodes) - n_users, embedding_dim,
+                    num_layers, init_weight[lo:hi], init_weight[n_users:], lr, betas, eps, alpha, group, backend, ld)
+
+    @staticmethod
+    def _pairs_layout_ok(edge_index: Tensor, n_users: int) -> bool:
+        if edge_index.size(1) % 2:
+            return False
+        e = edge_index.size(1) // 2
+        return bool(torch.equal(edge_index[0, :e], edge_index[1, e:]) and torch.equal(edge_index[1, :e], edge_index[0, e:])
+                    and (edge_index[0, :e] < n_users).all() and (edge_index[1, :e] >= n_users).all())
+
+    @classmethod
+    def from_pairs(cls, user: Tensor, item: Tensor, weight: Tensor, part: RowPartition, n_users: int, n_items: int,
+                   embedding_dim: int, num_layers: int, init_users: Tensor, init_items: Tensor, lr: float = 0.005,
+                   betas=(0.9, 0.999), eps: float = 1e-8, alpha=None, group=None, backend=None, ld=None):
+        """From this rank's OWN interactions only: `user` (global user ids inside the rank's range of
+        `part`), `item` (un-offset item ids), `weight`; `init_users` = the rank's rows of the initial
+        table, `init_items` = all item rows (replicated)."""
+        self = cls.__new__(cls)
+        self._setup(user, item, weight.float(), part, n_users, n_items, embedding_dim, num_layers, init_users,
+                    init_items, lr, betas, eps, alpha, group, backend, ld)
+        return self
+
+    def _setup(self, user, item, w, part, n_users, n_items, embedding_dim, num_layers, init_users, init_items, lr,
+               betas, eps, alpha, group, backend, ld):
         assert num_layers >= 1
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.backend = backend if backend is not None else CudaBackend()
-        self.dev = edge_index.device
-        self.num_nodes, self.dim, self.layers = int(num_nodes), int(embedding_dim), int(num_layers)
-        self.n_users, self.n_items = int(n_users), int(num_nodes) - int(n_users)
+        self.dev = user.device
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.num_nodes, self.dim, self.layers = self.n_users + self.n_items, int(embedding_dim), int(num_layers)
         if ld is None:
             from .graph import padded_dim
             ld = padded_dim(self.dim)
@@ -391,38 +469,46 @@ class BipartiteShardedTrainer(_GraphedStep):
         self.alpha = [float(a) for a in (alpha if alpha is not None else [1.0 / (num_layers + 1)] * (num_layers + 1))]
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.step_count = 0
+        self.part = part
+        lo, hi = part.lo(self.rank), part.hi(self.rank)
+        self.lo, self.hi, self.n_local, self.max_rows = lo, hi, hi - lo, part.max_rows
+        b, nu, ni = self.backend, self.max_rows, self.n_items
+        ul = user - lo
 
-        w_hat, deg, sym = self.backend.global_w_hat(edge_index, edge_weight, self.num_nodes)
-        if not sym:
-            raise RuntimeError("the sharded step needs a symmetric graph (backward reuses the operator)")
-        s = self.n_users
-        self.part = RowPartition(deg[:s].cpu().numpy(), self.world)          # users only
-        lo, hi = self.part.lo(self.rank), self.part.hi(self.rank)
-        self.lo, self.hi, self.n_local, self.max_rows = lo, hi, hi - lo, self.part.max_rows
-        src, dst = edge_index[0], edge_index[1]
-        to_user = (dst >= lo) & (dst < hi)                                   # item -> my user
-        to_item = (src >= lo) & (src < hi)                                   # my user -> item
-        self.gu = self.backend.build_rect(src[to_user] - s, dst[to_user] - lo, w_hat[to_user],
-                                          max(self.n_local, 1), self.n_items)
-        self.gi = self.backend.build_rect(src[to_item] - lo, dst[to_item] - s, w_hat[to_item],
-                                          self.n_items, self.max_rows)       # user tables have max_rows rows
-        self.local_nnz = int(to_user.sum().item()) + int(to_item.sum().item())
-        del w_hat, to_user, to_item
-        self.ws_u = self.backend.workspace(self.gu, ld, self.dev)
-        self.ws_i = self.backend.workspace(self.gi, ld, self.dev)
+        # ---- gcn_norm without the global graph: weighted in-degrees from the two local operators built on
+        # the RAW weights (users: all of a user's edges are local -> bit-exact; items: partial sums,
+        # all-reduced), then w_hat = (dis[src] * w) * dis[dst] per interaction, the same for both directions
+        g_u = b.build_rect(item, ul, w, max(self.n_local, 1), ni)
+        g_i = b.build_rect(ul, item, w, ni, nu)
+        deg_u = b.row_degree(g_u, max(self.n_local, 1), self.dev)
+        deg_i = b.row_degree(g_i, ni, self.dev)
+        b.destroy(g_u); b.destroy(g_i)
+        if self.world > 1:
+            dist.all_reduce(deg_i, group=self.group)
+        dis_u, dis_i = deg_u.pow(-0.5), deg_i.pow(-0.5)
+        dis_u[torch.isinf(dis_u)] = 0
+        dis_i[torch.isinf(dis_i)] = 0
+        w_ui = (dis_u[ul] * w) * dis_i[item]                   # edge user -> item (target item)
+        w_iu = (dis_i[item] * w) * dis_u[ul]                   # edge item -> user (target user)
+        self.gu = b.build_rect(item, ul, w_iu, max(self.n_local, 1), ni)
+        self.gi = b.build_rect(ul, item, w_ui, ni, nu)         # user tables have max_rows rows
+        self.local_nnz = 2 * int(user.numel())
+        del w_ui, w_iu, ul
+        self.ws_u = b.workspace(self.gu, ld, self.dev)
+        self.ws_i = b.workspace(self.gi, ld, self.dev)
 
         def table(rows):
             return torch.zeros(max(rows, 1), ld, dtype=torch.float32, device=self.dev)
-        nu, ni = self.max_rows, self.n_items
         self.e0_u, self.m_u, self.v_u = table(nu), table(nu), table(nu)
         self.e0_i, self.m_i, self.v_i = table(ni), table(ni), table(ni)
-        self.e0_u[: self.n_local, : self.dim] = init_weight[lo:hi].to(self.dev)
-        self.e0_i[:, : self.dim] = init_weight[s:].to(self.dev)
+        self.e0_u[: self.n_local, : self.dim] = init_users.to(self.dev)
+        self.e0_i[:, : self.dim] = init_items.to(self.dev)
         self.out_u, self.out_i = table(nu), table(ni)
-        self.xu, self.xi = [table(nu), table(nu)], [table(ni), table(ni)]
-        self.part_i = table(ni)                                              # partial item sums
+        n_x = max(self.layers - 1, 2)                           # stored layers (forward), ping-pong (backward)
+        self.xu, self.xi = [table(nu) for _ in range(n_x)], [table(ni) for _ in range(n_x)]
+        self.part_i = [table(ni), table(ni)]                    # partial item sums in flight (two layers)
         self.g_u, self.z_u, self.g_i, self.z_i = table(nu), table(nu), table(ni), table(ni)
-        self.n_cols = self.n_items                                           # rows exchanged per layer
+        self.n_cols = self.n_items                              # rows exchanged per layer
         self._init_graph_state()
 
     def __del__(self):
@@ -439,31 +525,43 @@ class BipartiteShardedTrainer(_GraphedStep):
         if self.world > 1:
             dist.all_reduce(t, group=self.group)
 
-    def _item_rows(self, x_u: Tensor, out: Tensor):
-        """out = (A_hat x)[items] = all-reduce of every rank's partial sums over its own users.
-        The all-reduce is ASYNCHRONOUS: the caller launches the (independent) user-row SpMM of the
-        same layer next and waits on the returned handle only when it needs the item rows, so the
-        NVLink exchange hides behind the HBM-bound kernel."""
+    def _item_partials(self, x_u: Tensor, out: Tensor):
+        """out = this rank's partial sums of (A_hat x)[items] over its own users, then the ASYNCHRONOUS
+        all-reduce of the partials; the caller waits on the returned handle only when it needs the item
+        rows, so the NVLink exchange hides behind the kernels issued in between."""
         self.backend.spmm_ex(self.gi, self.ld, x_u, self.ws_i, 0, y=out, scale=1.0)
         work = dist.all_reduce(out, group=self.group, async_op=True) if self.world > 1 else None
-        return out, work
+        return work
 
     # ------------------------------------------------------------------ forward only
     def propagate(self) -> Tuple[Tensor, Tensor]:
-        b, a, K = self.backend, self.alpha, self.layers
-        cu, ci = self.e0_u, self.e0_i
+        """out = sum_l alpha_l A_hat^l E0: user rows [max_rows, ld] (own users), item rows (replicated).
+        Layers 1..K-1 store x_l; layer K folds the whole mean into its epilogue (FWD_FINAL), for the
+        user rows inside the SpMM, for the item rows in one `lgc_epilogue_apply` after the all-reduce."""
+        b, a, K, ld = self.backend, self.alpha, self.layers, self.ld
+        hist_u, hist_i = [self.e0_u], [self.e0_i]
+        ci = self.e0_i
+        work = self._item_partials(self.e0_u, self.xi[0] if K > 1 else self.part_i[0])
         for l in range(1, K + 1):
             last = l == K
-            nu, ni = self.xu[l & 1], self.xi[l & 1]
-            yi, work = self._item_rows(cu, self.part_i if last else ni)
-            b.spmm_ex(self.gu, self.ld, ci, self.ws_u, 1 if l == 1 else 2, y=None if last else nu, acc=self.out_u,
-                      xrow=self.e0_u, a0=a[0], a1=a[l])
+            # user rows of layer l from the item rows of layer l-1
+            if last:
+                b.spmm_ex(self.gu, ld, ci, self.ws_u, 4, acc=self.out_u, a1=a[K], hist=hist_u, ah=a[:K])
+            else:
+                b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=self.xu[l - 1], scale=1.0)
+            # item partials of layer l+1 need only the user rows of layer l: issued BEFORE waiting for the
+            # all-reduce of layer l, which therefore overlaps both kernels
+            nwork = None
+            if not last:
+                nwork = self._item_partials(self.xu[l - 1], self.xi[l] if l + 1 < K else self.part_i[0])
             if work is not None:
                 work.wait()
-            if l == 1:
-                torch.mul(self.e0_i, a[0], out=self.out_i)
-            self.out_i.add_(yi, alpha=a[l])                    # replicated epilogue of the item rows
-            cu, ci = nu, ni
+            if last:
+                b.epilogue_apply(self.part_i[0], ld, 4, acc=self.out_i, a1=a[K], hist=hist_i, ah=a[:K])
+            else:
+                ci = self.xi[l - 1]                             # all-reduced in place: x_l of the items
+                hist_u.append(self.xu[l - 1]); hist_i.append(ci)
+                work = nwork
         return self.out_u, self.out_i
 
     # ------------------------------------------------------------------ one mini-batch
@@ -487,28 +585,26 @@ class BipartiteShardedTrainer(_GraphedStep):
         b.scatter_add(self.g_i, items, gc[batch:])           # replicated: bit-identical on every rank
         b.scatter_add(self.z_i, items, zc[batch:])
 
-        # ---- backward (Horner on the symmetric operator) + Adam
+        # ---- backward (Horner on the symmetric operator) + Adam: h_l = alpha_l G + A h_{l+1}
+        adam = dict(lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, **self._adam_kw())
         cu, ci, scale = self.g_u, self.g_i, a[K]
-        for l in range(K - 1, 0, -1):                         # h_l = alpha_l G + A h_{l+1}
-            nu, ni = self.xu[l & 1], self.xi[l & 1]
-            yi, work = self._item_rows(cu, ni)
-            b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=nu, addend=self.g_u, scale=scale, beta=a[l])
-            if work is not None:
-                work.wait()
-            if scale != 1.0:
-                yi.mul_(scale)
-            yi.add_(self.g_i, alpha=a[l])
-            cu, ci, scale = nu, ni, 1.0
-        yi, work = self._item_rows(cu, self.part_i)
-        b.spmm_ex(self.gu, ld, ci, self.ws_u, 3, addend=self.z_u, scale=scale, p=self.e0_u, m=self.m_u, v=self.v_u,
-                  lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, **self._adam_kw())
-        if work is not None:
-            work.wait()
-        if scale != 1.0:
-            yi.mul_(scale)
-        yi.add_(self.z_i)
-        b.adam_step(self.e0_i, yi, self.m_i, self.v_i, self.lr, self.betas, self.eps, self.step_count,
-                    **self._adam_kw())
+        work = self._item_partials(cu, self.part_i[0])
+        for l in range(K - 1, -1, -1):
+            pi = self.part_i[(K - 1 - l) & 1]
+            if l > 0:
+                nu_, ni_ = self.xu[l & 1], self.xi[l & 1]
+                b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=nu_, addend=self.g_u, scale=scale, beta=a[l])
+                nwork = self._item_partials(nu_, self.part_i[(K - l) & 1])      # item partials of the next layer
+                if work is not None:
+                    work.wait()
+                b.epilogue_apply(pi, ld, 0, y=ni_, addend=self.g_i, scale=scale, beta=a[l])
+                cu, ci, scale, work = nu_, ni_, 1.0, nwork
+            else:
+                b.spmm_ex(self.gu, ld, ci, self.ws_u, 3, addend=self.z_u, scale=scale, p=self.e0_u, m=self.m_u,
+                          v=self.v_u, **adam)
+                if work is not None:
+                    work.wait()
+                b.epilogue_apply(pi, ld, 3, addend=self.z_i, scale=scale, p=self.e0_i, m=self.m_i, v=self.v_i, **adam)
         self.g_u.index_fill_(0, locc, 0.0)
         self.z_u.index_fill_(0, locc, 0.0)
         self.g_i.index_fill_(0, items, 0.0)

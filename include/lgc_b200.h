@@ -141,8 +141,12 @@ int lgc_spmm(const lgc_graph_t* graph, int ld, const float* x, float* y, void* w
  *   LGC_EPI_PLAIN    y = scale * s + beta * addend            (addend may be NULL)
  *   LGC_EPI_FWD_INIT acc = a0 * xrow + a1 * s;  y = s if y != NULL
  *   LGC_EPI_FWD_RMW  acc = acc + a1 * s;        y = s if y != NULL
- *   LGC_EPI_ADAM     g = scale * s + addend; torch.optim.Adam update of p, m, v with g */
-typedef enum { LGC_EPI_PLAIN = 0, LGC_EPI_FWD_INIT = 1, LGC_EPI_FWD_RMW = 2, LGC_EPI_ADAM = 3 } lgc_epilogue_mode;
+ *   LGC_EPI_ADAM     g = scale * s + addend; torch.optim.Adam update of p, m, v with g
+ *   LGC_EPI_FWD_FINAL acc = (((hist[0]*ah[0] + hist[1]*ah[1]) + ...) + a1 * s): the whole layer mean of
+ *                    get_embedding (src/lightgcn.py:91-99) in the LAST layer's epilogue, from the
+ *                    n_hist stored layer tables (E0, x_1, ..., x_{K-1}), same rounding sequence */
+typedef enum { LGC_EPI_PLAIN = 0, LGC_EPI_FWD_INIT = 1, LGC_EPI_FWD_RMW = 2, LGC_EPI_ADAM = 3,
+               LGC_EPI_FWD_FINAL = 4 } lgc_epilogue_mode;
 typedef struct {
   int32_t mode;
   float a0, a1, scale, beta;
@@ -157,9 +161,17 @@ typedef struct {
   int64_t step;
   const float* adam_scalars;   /* optional DEVICE pointer to the 6 floats of lgc_adam_scalars(): lets a
                                   captured CUDA graph replay the launch with a new step count */
+  const float* hist[6];        /* LGC_EPI_FWD_FINAL: layer tables x_0 .. x_{n_hist-1} ([rows, ld])        */
+  float ah[6];                 /*                    their weights alpha_0 .. alpha_{n_hist-1}            */
+  int32_t n_hist;
 } lgc_spmm_epilogue;
 int lgc_spmm_ex(const lgc_graph_t* graph, int ld, const float* x, const lgc_spmm_epilogue* epilogue,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same fused epilogues applied to row sums that already exist: `sums` is a dense [n_rows, ld] table
+ * (row r of `sums` plays the role of (A_hat x)[r]). The multi-GPU step uses it for the replicated item
+ * rows, whose sums arrive through the all-reduce of the ranks' partial sums. */
+int lgc_epilogue_apply(int64_t n_rows, int ld, const float* sums, const lgc_spmm_epilogue* epilogue, void* stream);
 
 /* ------------------------------------------------------------------ get_embedding (src/lightgcn.py:91-99)
  * out = sum_{l=0..K} alpha_l A_hat^l x0, evaluated like the reference as a running sum but

@@ -26,12 +26,26 @@ class CpuCheckBackend:
     def workspace(self, handle, ld, device):
         return torch.empty(1)
 
-    def spmm_ex(self, h, ld, x, ws, mode, *, y=None, acc=None, xrow=None, addend=None, a0=0.0, a1=0.0, scale=1.0,
-                beta=0.0, p=None, m=None, v=None, lr=0.0, betas=(0.9, 0.999), eps=1e-8, step=1, adam_scalars=None):
+    def row_degree(self, h, n_rows, device):
+        return torch.zeros(h["n_rows"]).index_add_(0, h["dst"], h["w"])[:n_rows]    # sequential: edge order
+
+    def spmm_ex(self, h, ld, x, ws, mode, **kw):
         n = h["n_rows"]
         assert x.shape == (h["n_cols"], ld)
         s = torch.zeros(n, ld).index_add_(0, h["dst"], h["w"][:, None] * x[h["src"]])
+        self.epilogue_apply(s, ld, mode, **kw)
+
+    def epilogue_apply(self, s, ld, mode, *, y=None, acc=None, xrow=None, addend=None, a0=0.0, a1=0.0, scale=1.0,
+                       beta=0.0, p=None, m=None, v=None, lr=0.0, betas=(0.9, 0.999), eps=1e-8, step=1,
+                       adam_scalars=None, hist=None, ah=None):
+        n = s.size(0)
         f = torch.float32
+        if mode == 4:
+            r = hist[0][:n] * torch.tensor(ah[0], dtype=f)
+            for t, w in zip(hist[1:], ah[1:]):
+                r = r + t[:n] * torch.tensor(w, dtype=f)
+            acc[:n] = r + s * torch.tensor(a1, dtype=f)
+            return
         if mode == 0:
             r = torch.tensor(scale, dtype=f) * s
             if addend is not None:
