@@ -272,12 +272,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c5"],
+                    help="c5 (16 M users x 500 K items, 200 M interactions) is generated per rank: use --gpus 8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--no-epoch", action="store_true", help="skip the measured epoch (sampler + steps + eval)")
     ap.add_argument("--only-scoring", action="store_true", help="skip the training-step timing (dev aid)")
     ap.add_argument("--score-users", type=int, default=0, help="0 = all users (c4)")
+    ap.add_argument("--c5-scale", type=float, default=1.0, help="shrink c5 by this factor (development aid)")
     ap.add_argument("--shard-mode", default="auto", choices=["auto", "bipartite", "rows"],
                     help="N > 1: how the training step is sharded")
     args = ap.parse_args()
@@ -310,6 +312,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
     pk = peaks()
+    if args.config == "c5":
+        return bench_c5(args, world, rank, dev, lib, pk)
 
     n_batches = args.steps + args.warmup
     g, dim, layers, init, triples = make_workload(args.config, n_batches)
@@ -528,6 +532,174 @@ def main():
         "cpu_baseline": cpu,
         "scoring": score,
     }
+    emit(line)
+    return finish(world, trainer)
+
+
+def bench_c5(args, world, rank, dev, lib, pk):
+    """c5, the scale-up stress of BASELINE.json: 16 M users x 500 K items, 200 M weighted interactions,
+    K = 3, d = 64, propagation + BPR step across the GPUs of one box. No process ever holds the global
+    edge list: every rank generates ITS OWN users' interactions (same generator and weight law as c2,
+    seeded per rank), builds its two rectangular operators from them, and the item degrees are the
+    all-reduced partial degrees. Triples: every rank samples batch / world triples among its own
+    purchasers (`batch_loader` semantics), all-gathered into the global batch.
+    Parity at this size: 64 sampled user rows and 64 sampled item rows of the FIRST propagation layer
+    against an fp64 numpy evaluation of the definition from the raw interactions (the item rows need
+    every rank's edges: partial sums, all-reduced)."""
+    import torch
+    import torch.distributed as dist
+    from gnn_ecommerce_b200 import synth
+    from gnn_ecommerce_b200.graph import padded_dim
+    from gnn_ecommerce_b200.sharded import BipartiteShardedTrainer, RowPartition
+    n_users, n_items, n_edges, dim, layers = synth.CONFIGS["c5"]
+    if args.c5_scale != 1.0:                      # a smaller stress of the same shape (development aid)
+        n_users, n_items, n_edges = (int(x * args.c5_scale) for x in (n_users, n_items, n_edges))
+    assert n_users % world == 0 and n_edges % world == 0
+    nu, ne = n_users // world, n_edges // world
+    t0 = time.time()
+    g = synth.make_graph(nu, n_items, ne, seed=4200 + rank)          # this rank's users: local ids 0..nu-1
+    log(f"[bench] rank {rank}: c5 shard {nu} users x {n_items} items, {ne} interactions ({time.time() - t0:.1f}s)")
+    part = RowPartition(np.ones(n_users), world)
+    part.bounds = np.arange(world + 1, dtype=np.int64) * nu
+    part.max_rows = (nu + 3) // 4 * 4
+    lo = rank * nu
+    user = torch.from_numpy(g.user + lo).to(dev)
+    item = torch.from_numpy(g.item - nu).to(dev)
+    w = torch.from_numpy(g.weight).to(dev)
+    bound = np.sqrt(6.0 / (n_users + n_items + dim))
+    init_u = torch.from_numpy(np.random.default_rng(4300 + rank).uniform(-bound, bound, (nu, dim)).astype(np.float32))
+    init_i = torch.from_numpy(np.random.default_rng(4299).uniform(-bound, bound, (n_items, dim)).astype(np.float32))
+    trainer = BipartiteShardedTrainer.from_pairs(user, item, w, part, n_users, n_items, dim, layers, init_u, init_i,
+                                                 lr=LR)
+    ld = padded_dim(dim)
+    nnz = 2 * n_edges
+
+    # ---- parity of sampled rows of layer 1 (x1 = A_hat E0) against fp64 numpy from the raw interactions
+    info = {}
+    if True:
+        b = trainer.backend
+        x1_u = torch.zeros_like(trainer.e0_u)
+        x1_i = torch.zeros_like(trainer.e0_i)
+        b.spmm_ex(trainer.gu, ld, trainer.e0_i, trainer.ws_u, 0, y=x1_u, scale=1.0)
+        b.spmm_ex(trainer.gi, ld, trainer.e0_u, trainer.ws_i, 0, y=x1_i, scale=1.0)
+        if world > 1:
+            dist.all_reduce(x1_i)
+        gu_l, gi_l, gw = g.user.astype(np.int64), (g.item - nu).astype(np.int64), g.weight.astype(np.float64)
+        # the fp32 deg^-1/2 the step itself uses (gcn_norm sums the weighted degree in fp32: for a hub item
+        # with millions of edges that sum alone is ~1e-5 away from fp64, on one GPU as well): the check
+        # isolates the propagation, w_hat = (dis[src] * w) * dis[dst] evaluated in fp64 from those
+        dis_u = trainer.dis_u.double().cpu().numpy()
+        dis_i = trainer.dis_i.double().cpu().numpy()
+        what = dis_u[gu_l] * gw * dis_i[gi_l]
+        rng = np.random.default_rng(99)
+        su = rng.choice(nu, 64, replace=False)
+        si = np.random.default_rng(98).choice(n_items, 64, replace=False)          # same items on every rank
+        e0u, e0i = init_u.numpy().astype(np.float64), init_i.numpy().astype(np.float64)
+        want_u = np.zeros((64, dim))
+        for j, u_ in enumerate(su):
+            m_ = gu_l == u_
+            want_u[j] = (what[m_, None] * e0i[gi_l[m_]]).sum(0)
+        part_i = np.zeros((64, dim))
+        for j, i_ in enumerate(si):
+            m_ = gi_l == i_
+            part_i[j] = (what[m_, None] * e0u[gu_l[m_]]).sum(0)
+        want_i = torch.from_numpy(part_i).to(dev)
+        if world > 1:
+            dist.all_reduce(want_i)
+        got_u = x1_u[torch.from_numpy(su).to(dev), :dim].double().cpu().numpy()
+        got_i = x1_i[torch.from_numpy(si).to(dev), :dim].double()
+        err_u = float(np.abs(got_u - want_u).max() / np.abs(want_u).max())
+        err_i = float((got_i - want_i).abs().max() / want_i.abs().max())
+        info = {"layer1_sampled_rows": 128, "max_rel_err_user_rows": err_u, "max_rel_err_item_rows": err_i,
+                "bar": 1e-5, "ok": bool(err_u < 1e-5 and err_i < 1e-5)}
+        log(f"[bench] rank {rank}: c5 layer-1 parity of sampled rows: users {err_u:.2e}, items {err_i:.2e}")
+        del x1_u, x1_i
+
+    # ---- triples: batch / world per rank among its own purchasers, all-gathered
+    pl = synth.purchase_lists(g)
+    per = BATCH // world
+    rng = np.random.default_rng(4400 + rank)
+    n_batches = args.steps + args.warmup
+    dev_triples = []
+    for _ in range(n_batches):
+        u_, p_, n_ = synth.sample_triples(pl, per, nu, n_items, rng)
+        mine = torch.from_numpy(np.stack([u_ + lo, p_ - nu + n_users, n_ - nu + n_users])).to(dev)
+        if world > 1:
+            allt = torch.empty(world, 3, per, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allt, mine)
+            mine = allt.permute(1, 0, 2).reshape(3, world * per)
+        dev_triples.append((mine[0].contiguous(), mine[1].contiguous(), mine[2].contiguous()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        trainer.step(*dev_triples[i], DECAY)
+    barrier()
+    launches0 = lib.lgc_launch_count()
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index or 0) as clocks:
+        beg.record()
+        for i in range(args.steps):
+            loss3 = trainer.step(*dev_triples[args.warmup + i], DECAY)
+        end.record()
+        barrier()
+    ms_total = beg.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    # end to end: host triples in, losses out, every step
+    pin = [tuple(x.cpu().pin_memory() for x in t) for t in dev_triples]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        u_, p_, n_ = (x.to(dev, non_blocking=True) for x in pin[args.warmup + i])
+        host_losses = trainer.step(u_, p_, n_, DECAY).cpu()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    trainer.use_graph = False
+    eager0 = lib.lgc_launch_count()
+    trainer.step(*dev_triples[0], DECAY)
+    torch.cuda.synchronize()
+    launches = (lib.lgc_launch_count() - eager0) * args.steps
+    trainer.use_graph = True
+    if rank != 0:
+        return finish(world, trainer)
+    n_nodes = n_users + n_items
+    idx = nnz * 8 + (n_nodes + 1) * 4
+    tbytes = n_nodes * ld * 4
+    step_bytes = 2 * (layers * idx + (4 * layers - 1) * tbytes) + 7 * tbytes
+    gbs = step_bytes / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": "lgconv_gedges_per_s", "value": nnz * 2 * layers / (ms_step * 1e-3) / 1e9, "unit": "GEdges/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c5: LightGCN K={layers} d={dim}, N={n_nodes}, nnz={nnz}, batch={BATCH}, "
+                               f"full training step (fwd+BPR+bwd+Adam)",
+                   "l2": "inputs (>= 4 GB of tables per rank and step) exceed the 126 MB L2; no flush",
+                   "steps_per_epoch": int(n_edges / (BATCH * 40)),
+                   "parallelism": f"users partitioned over {world} GPUs (each rank generated and holds only its own "
+                                  f"users' interactions), item table replicated, NCCL all-reduce of the item partial "
+                                  f"sums per layer"},
+        "epoch_s": ms_step * int(n_edges / (BATCH * 40)) * 1e-3,
+        "losses_last_step": [float(x) for x in loss3.cpu().tolist()],
+        "e2e": {"value": nnz * 2 * layers * args.steps / e2e_s / 1e9, "unit": "GEdges/s",
+                "h2d_bytes_per_step": 3 * BATCH * 8, "d2h_bytes_per_step": 12, "ms_per_step": e2e_s / args.steps * 1e3,
+                "losses_last_step": [float(x) for x in host_losses.tolist()]},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "kernel": "whole step, all ranks", "achieved": gbs, "peak": pk["hbm_gbs"] * world,
+                     "unit": "GB/s", "frac": gbs / (pk["hbm_gbs"] * world), "traffic": None,
+                     "peak_source": pk["source"], "step_algorithmic_bytes": step_bytes,
+                     "nvlink_bytes_per_step_per_gpu": 2 * layers * n_items * ld * 4 * 2 * (world - 1) // max(world, 1)},
+        "parity": info, "cpu_baseline": None, "scoring": None}
     emit(line)
     return finish(world, trainer)
 

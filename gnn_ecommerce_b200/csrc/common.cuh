@@ -61,6 +61,15 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_record(tag, st, false); }
 };
 
+// NVTX ranges around the C-ABI entry points (LGC_NVTX=1): what an nsys / ncu --nvtx timeline of a
+// training or scoring run is read by (the reference has no tracing at all).
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtx_push(name); }
+  ~NvtxRange() { nvtx_pop(); }
+};
+
 constexpr int kNumSMs = 148;  // B200 (grid sizing of the small helper kernels)
 constexpr int kMaxDevices = 64;
 

@@ -2,7 +2,9 @@
 // Runs once per graph; replaces the degree normalisation PyG recomputes in every LGConv call
 // (reference call site src/lightgcn.py:96; input layout src/utils_v2.py:146-165).
 #include <cub/cub.cuh>
+#include <nvtx3/nvToolsExt.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -13,6 +15,13 @@ thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 long long g_launch_count = 0;
+
+static bool nvtx_on() {
+  static const bool on = [] { const char* e = getenv("LGC_NVTX"); return e && atoi(e) != 0; }();
+  return on;
+}
+void nvtx_push(const char* name) { if (nvtx_on()) nvtxRangePushA(name); }
+void nvtx_pop() { if (nvtx_on()) nvtxRangePop(); }
 
 struct ProfEvent { int tag; cudaEvent_t beg, end; };
 static bool g_prof_on = false;
@@ -287,6 +296,7 @@ template <class Edges>
 static int graph_build_impl(int64_t num_nodes, int64_t num_cols, int64_t nnz, Edges edges,
                             int normalize, void* stream_, lgc_graph_t** out) {
   LGC_REQUIRE(out, "out_graph is null");
+  NvtxRange nvtx("lgc_graph_build");
   *out = nullptr;
   LGC_REQUIRE(num_nodes > 0 && num_nodes < (1LL << 31) - 64, "num_nodes out of range");
   LGC_REQUIRE(num_cols > 0 && num_cols < (1LL << 31) - 64, "num_cols out of range");

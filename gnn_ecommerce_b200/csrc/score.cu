@@ -1175,6 +1175,7 @@ extern "C" size_t lgc_score_topk_workspace_bytes(int64_t n_users, int64_t n_item
 }
 
 extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
+  NvtxRange nvtx("lgc_score_topk");
   LGC_REQUIRE(a, "null argument");
   LGC_REQUIRE(a->user_emb && a->item_emb && a->topk_items && a->workspace, "null field in lgc_score_topk_args");
   LGC_REQUIRE(a->d >= 1 && a->d <= a->ld_user && a->d <= a->ld_item, "d must fit both row strides");

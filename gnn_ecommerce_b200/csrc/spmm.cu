@@ -1118,6 +1118,7 @@ extern "C" int lgc_propagate(const lgc_graph_t* g, int ld, int num_layers, const
     set_error("lgc_propagate: workspace too small");
     return LGC_ERR_WORKSPACE;
   }
+  NvtxRange nvtx("lgc_propagate");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t t = (size_t)g->num_nodes * ld;
   if (num_layers == 0) {

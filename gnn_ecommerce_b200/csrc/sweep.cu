@@ -192,6 +192,7 @@ struct Dev {
   } while (0)
 
 SweepSched* sweep_build(const lgc_graph* g, int S) {
+  NvtxRange nvtx("lgc_sweep_schedule_build");
   int dev = 0, n_sms = 0;
   SWEEP_CUDA(cudaGetDevice(&dev));
   SWEEP_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -108,6 +108,7 @@ extern "C" int lgc_train_step(const lgc_graph_t* g, const lgc_train_step_args* a
     set_error("lgc_train_step: workspace too small");
     return LGC_ERR_WORKSPACE;
   }
+  NvtxRange nvtx("lgc_train_step");
   cudaStream_t st = (cudaStream_t)stream;
   const int ld = a->ld, K = a->num_layers;
   const float* alpha = a->h_alpha;

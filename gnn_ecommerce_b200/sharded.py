@@ -488,6 +488,7 @@ class BipartiteShardedTrainer(_GraphedStep):
         dis_u, dis_i = deg_u.pow(-0.5), deg_i.pow(-0.5)
         dis_u[torch.isinf(dis_u)] = 0
         dis_i[torch.isinf(dis_i)] = 0
+        self.dis_u, self.dis_i = dis_u, dis_i                  # deg^-1/2 (fp32, like gcn_norm): kept for checks
         w_ui = (dis_u[ul] * w) * dis_i[item]                   # edge user -> item (target item)
         w_iu = (dis_i[item] * w) * dis_u[ul]                   # edge item -> user (target user)
         self.gu = b.build_rect(item, ul, w_iu, max(self.n_local, 1), ni)

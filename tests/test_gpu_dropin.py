@@ -161,3 +161,26 @@ def test_reference_torchserve_handler_over_the_dropin_module(tmp_path):
     want = h_r.model.recommendK(t_r.edge_index, t_r.edge_weight, t_r.n_users, t_r.n_items, mask, users, K)
     agree2 = np.mean([len(set(a) & set(b)) / K for a, b in zip(svc2.inference(users)["items"], want["top_rlvnt_itm"])])
     assert agree2 > 0.99, agree2
+
+
+def test_device_sampler_from_the_reference_train_pos_list_frame(tmp_path):
+    """`DeviceSampler.from_frame` on the `train_pos_list_df` the reference's own `prepare_val_test` builds
+    (src/utils_v2.py:106-143): every triple obeys `batch_loader` (:168-181) -- distinct purchasers, the
+    positive from the user's `item_id_idx_list`, the negative outside its `ignor_neg_list`."""
+    from gnn_ecommerce_b200.sampler import DeviceSampler
+    (_, t_o, _), _ = _trainers(str(tmp_path))
+    frame = t_o.train_pos_list_df
+    sampler = DeviceSampler.from_frame(frame, t_o.n_users, t_o.n_items, DEV, seed=3)
+    pos_of = dict(zip(frame["user_id_idx"], frame["item_id_idx_list"]))
+    ign_of = dict(zip(frame["user_id_idx"], frame["ignor_neg_list"]))
+    seen_users = set()
+    for _ in range(4):
+        u, p, n = (x.cpu().numpy() for x in sampler.sample(256))
+        assert len(set(u.tolist())) == 256 and set(u.tolist()) <= set(pos_of)
+        for uu, pp, nn_ in zip(u, p, n):
+            assert pp in pos_of[uu]
+            assert nn_ not in set(ign_of[uu]) and t_o.n_users <= nn_ < t_o.n_users + t_o.n_items
+        seen_users |= set(u.tolist())
+    assert len(seen_users) > 600                    # batches differ
+    with pytest.raises(ValueError):                 # random.sample: "Sample larger than population"
+        sampler.sample(len(frame) + 1)
