@@ -26,6 +26,9 @@ namespace lgc {
 namespace {
 
 constexpr int kRowsThreads = 256;
+#ifndef LGC_ROWS_L64
+#define LGC_ROWS_L64 8
+#endif
 #ifndef LGC_ROWS_G
 #define LGC_ROWS_G 2
 #endif
@@ -206,7 +209,7 @@ int launch_rows(const lgc_graph* g, const RowPlan* plan, int ld, const float* x,
   // sub-warp geometry per row width: L lanes x V float4 (few lanes per row: more rows per warp instruction)
 #define LGC_ROWS_CASE(LDV, LL, LV) case LDV: rc = launch_rows_lv<LL, LV>(plan, x, mode, a, g->rowptr, st); break;
   switch (ld) {
-    LGC_ROWS_CASE(64, 8, 2) LGC_ROWS_CASE(128, 16, 2) LGC_ROWS_CASE(192, 16, 3) LGC_ROWS_CASE(256, 16, 4)
+    LGC_ROWS_CASE(64, LGC_ROWS_L64, 16 / LGC_ROWS_L64) LGC_ROWS_CASE(128, 16, 2) LGC_ROWS_CASE(192, 16, 3) LGC_ROWS_CASE(256, 16, 4)
     LGC_ROWS_CASE(32, 8, 1) LGC_ROWS_CASE(96, 8, 3) LGC_ROWS_CASE(160, 8, 5)
     LGC_ROWS_CASE(16, 4, 1) LGC_ROWS_CASE(48, 4, 3) LGC_ROWS_CASE(80, 4, 5)
     default: break;
