@@ -842,11 +842,14 @@ def bench_scoring(rows, g, dev, args, pk, dim, world=1, rank=0):
             mask[i, seen.items[int(lo[i]):int(hi[i])]] = 1.0
         ref = pred * (1 - mask)
         ref_kth = ref.topk(k, dim=-1).values[:, -1]
-        got_scores = torch.gather(ref, 1, top[chk])
+        got = top[chk]
+        invalid = int(((got < 0) | (got >= g.n_items)).any(dim=-1).sum())      # ids outside [0, n_items)
+        got_scores = torch.gather(ref, 1, got.clamp(0, g.n_items - 1))
         tol = 2e-6 * ref.abs().amax(dim=-1)
         bad = int(((got_scores.min(dim=-1).values + tol) < ref_kth).sum())
         dup = int((torch.sort(top[chk], dim=-1).values.diff(dim=-1) == 0).any(dim=-1).sum())
     check = {"users_checked": n_chk, "users_with_a_wrong_item": bad, "users_with_duplicates": dup,
+             "users_with_invalid_ids": invalid,
              "host_array_matches_device": bool((torch.from_numpy(host_top.astype(np.int64)).to(dev) == top_e).all())}
     flops_local = 2.0 * (u1 - u0) * g.n_items * dim
     flops = 2.0 * n_score * g.n_items * dim

@@ -61,11 +61,14 @@ __device__ __forceinline__ void rows_group(const int2 my, int t0, int n, const f
     }
 }
 
-template <int L, int V, int MODE, bool XM>   // XM: args.x_mask marks the source rows that are not zero
+// XM: args.x_mask marks the source rows that are not zero; SPLIT: a block's passes are dealt to `split`
+// work items (false: split == 1, the compile-time constant keeps the large-graph code as it was)
+template <int L, int V, int MODE, bool XM, bool SPLIT>
 __global__ void __launch_bounds__(kRowsThreads, (MODE == EPI_ADAM || MODE == EPI_FWD_FINAL || V > 2) ? 3 : 4)
 k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, const uint8_t* __restrict__ perm,
-            const int32_t* __restrict__ blk_cnt, int n_blocks, int num_rows, const float* __restrict__ x,
-            EpiArgs args) {
+            const int32_t* __restrict__ blk_cnt, int n_blocks, int split_arg, int num_rows,
+            const float* __restrict__ x, EpiArgs args) {
+  const int split = SPLIT ? split_arg : 1;
   constexpr int LD = 4 * L * V, NSUB = 32 / L, SUBS = (kRowsThreads / 32) * NSUB, G = LGC_ROWS_G;
   static_assert(kRowsThreads == kRowsBlock, "one thread loads one row's metadata");
   __shared__ int s_rp[2][kRowsBlock + 1];
@@ -75,8 +78,11 @@ k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, co
   const int sub = wic * NSUB + sw;
   const float* const xl = x + 4 * sl;
   int buf = 0;
+  // work item = (block, part): a block's passes are dealt round-robin to `split` items (1 on large
+  // graphs; 2 or 4 when there are too few blocks to fill every CTA slot evenly, e.g. one rank's users)
 #pragma unroll 1
-  for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, buf ^= 1) {
+  for (int item = blockIdx.x; item < n_blocks * split; item += gridDim.x, buf ^= 1) {
+    const int b = item / split, part = item - b * split;
     const int row0 = b * kRowsBlock;
     const int cnt = blk_cnt[b];
     s_rp[buf][tid] = rowptr[min(row0 + tid, num_rows)];
@@ -105,14 +111,14 @@ k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, co
         }
       }
     };
-    fetch(0, 0);
+    fetch(part * SUBS, 0);
     int pass = 0;
 #pragma unroll 1
-    for (int j0 = 0; j0 < cnt; j0 += SUBS, ++pass) {
+    for (int j0 = part * SUBS; j0 < cnt; j0 += split * SUBS, ++pass) {
       const int r = r_n, e0 = e0_n, deg = deg_n;      // deg < 0: no row for this sub-warp in this pass
       const bool valid = deg >= 0;
       int2 my = my_n;
-      fetch(j0 + SUBS, pass + 1);
+      fetch(j0 + split * SUBS, pass + 1);
       const int dmax = __reduce_max_sync(0xffffffffu, deg);
       const size_t off = (size_t)r * LD + 4 * sl;
       EpiPre<MODE, 4> pre[V];
@@ -162,8 +168,9 @@ int launch_rows_lvmx(const RowPlan* p, const float* x, const EpiArgs& a, const i
   int occ = (dev >= 0 && dev < 64) ? occ_dev[dev] : 0;
   static int sms_dev[64] = {};
   if (!occ) {
-    LGC_CUDA(cudaFuncSetAttribute(k_spmm_rows<L, V, MODE, XM>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));   // ~36 KB of shared memory, the rest L1
-    LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_rows<L, V, MODE, XM>, kRowsThreads, 0));
+    LGC_CUDA(cudaFuncSetAttribute(k_spmm_rows<L, V, MODE, XM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
+    LGC_CUDA(cudaFuncSetAttribute(k_spmm_rows<L, V, MODE, XM, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 16));   // ~36 KB of shared memory, the rest L1
+    LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_rows<L, V, MODE, XM, false>, kRowsThreads, 0));
     if (occ < 1) occ = 1;
     int sms = 0;
     LGC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -171,11 +178,24 @@ int launch_rows_lvmx(const RowPlan* p, const float* x, const EpiArgs& a, const i
     else sms_dev[0] = sms;
   }
   const int sms = (dev >= 0 && dev < 64) ? sms_dev[dev] : sms_dev[0];
-  const int grid = (int)std::min<int64_t>((int64_t)sms * occ, p->n_blocks);
+  const int64_t slots = (int64_t)sms * occ;
+  // few blocks (one rank's users): finer work items, when the waves then come out shorter. Rounds of work
+  // per CTA slot in units of whole blocks, plus ~8 % per extra part for re-reading the block's metadata
+  int split = 1;
+  double best = 1e30;
+  for (int c = 1; c <= 4; c *= 2) {
+    const double cost = (double)ceil_div(p->n_blocks * c, slots) / c * (1.0 + 0.08 * (c - 1));
+    if (cost < best - 1e-9) { best = cost; split = c; }
+  }
+  const int grid = (int)std::min<int64_t>(slots, p->n_blocks * split);
   if (grid <= 0) return LGC_OK;
   ProfScope ps(PROF_LIGHT + (MODE & 3), st);
-  k_spmm_rows<L, V, MODE, XM><<<grid, kRowsThreads, 0, st>>>(rowptr, p->rec, p->perm, p->blk_cnt, (int)p->n_blocks,
-                                                         (int)p->num_rows, x, a);
+  if (split == 1)
+    k_spmm_rows<L, V, MODE, XM, false><<<grid, kRowsThreads, 0, st>>>(rowptr, p->rec, p->perm, p->blk_cnt,
+                                                                      (int)p->n_blocks, 1, (int)p->num_rows, x, a);
+  else
+    k_spmm_rows<L, V, MODE, XM, true><<<grid, kRowsThreads, 0, st>>>(rowptr, p->rec, p->perm, p->blk_cnt,
+                                                                     (int)p->n_blocks, split, (int)p->num_rows, x, a);
   return LGC_OK;
 }
 

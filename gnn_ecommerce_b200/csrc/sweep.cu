@@ -213,7 +213,7 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
   // A rectangular operator whose rows all fit (the item-partial operator of the multi-GPU step: every
   // item row, few edges each per rank) goes to the sweep entirely: one launch instead of two, and the
   // rows with few LOCAL edges still share the window of the source table with the hubs.
-  const bool all_rows = with_plan && g->num_cols != g->num_nodes && n <= (int64_t)n_units * S * 8 / 10;
+  const bool all_rows = with_plan && g->num_cols != g->num_nodes && n <= (int64_t)n_units * S * 9 / 10;
   const int threshold = all_rows ? -1 : (with_plan ? rows_max_degree : g->light_max_degree);
   std::vector<int32_t> rows;
   for (int64_t r = 0; r < n; ++r)
@@ -239,7 +239,7 @@ SweepSched* sweep_build(const lgc_graph* g, int S) {
     n_pieces = 0;
     for (size_t i = 0; i < rows.size(); ++i) {
       const int d = rp[rows[i] + 1] - rp[rows[i]];
-      r_pieces[i] = (int32_t)((d + piece_max - 1) / piece_max);
+      r_pieces[i] = (int32_t)std::max<int64_t>(1, (d + piece_max - 1) / piece_max);   // a row without edges still owns a slot (its epilogue)
       n_pieces += r_pieces[i];
     }
     if (n_pieces <= (int64_t)n_units * S) break;
@@ -524,17 +524,27 @@ k_spmm_sweep(const int32_t* __restrict__ warp_ptr, const int2* __restrict__ rec,
   __syncwarp();
 
   // ---- epilogue: the unit's rows leave shared memory through the fused epilogue (or as partial rows)
+  // (the unit's row table is read 16 entries at a time, one per lane, and handed round with shuffles:
+  // S dependent global loads in a row made this tail as long as the sweep itself on small operators)
   const int2* ur = unit_rows + (size_t)(warp * 2 + half) * S;
-  for (int s = 0; s < S; ++s) {
-    const int2 d = ur[s];
-    if (d.x < 0) continue;
+  for (int s0 = 0; s0 < S; s0 += 16) {
+    int2 q = make_int2(-1, -1);
+    if (s0 + l16 < S) q = __ldg(ur + s0 + l16);
+    const int n_here = min(16, S - s0);
+    for (int j = 0; j < n_here; ++j) {
+      int2 d;
+      d.x = __shfl_sync(0xffffffffu, q.x, (lane & 16) + j);
+      d.y = __shfl_sync(0xffffffffu, q.y, (lane & 16) + j);
+      if (d.x < 0) continue;
+      const int s = s0 + j;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      float t[W];
-      ldv<W>(my + s * LD + 16 * W * k, t);
-      const int col = W * l16 + 16 * W * k;
-      if (d.y >= 0) stv<W>(partials + (size_t)d.y * LD + col, t);
-      else epilogue_w<MODE, W>(args, (size_t)d.x * LD + col, t);
+      for (int k = 0; k < NV; ++k) {
+        float t[W];
+        ldv<W>(my + s * LD + 16 * W * k, t);
+        const int col = W * l16 + 16 * W * k;
+        if (d.y >= 0) stv<W>(partials + (size_t)d.y * LD + col, t);
+        else epilogue_w<MODE, W>(args, (size_t)d.x * LD + col, t);
+      }
     }
   }
 }

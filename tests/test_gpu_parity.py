@@ -442,3 +442,28 @@ def test_resume_from_a_checkpoint_written_by_the_reference():
     loss3 = trainer.step(ei, ew, u, p, n, DECAY).cpu().numpy()
     assert np.allclose(loss3, nxt["losses"], rtol=1e-5, atol=0), (loss3, nxt["losses"])
     assert rel(model.embedding.weight.detach().cpu().numpy(), nxt["w3"]) < 1e-5
+
+
+def test_rectangular_operator_entirely_in_the_sweep_with_empty_rows():
+    """The item-partial operator of the multi-GPU step: a small rectangular operator goes to the sweep
+    kernel as a whole, including rows WITHOUT local edges (an item none of this rank's users touched),
+    which must come out as exact zeros / as the pure epilogue."""
+    from gnn_ecommerce_b200.sharded import CudaBackend
+    be = CudaBackend()
+    rng = np.random.default_rng(8)
+    n_rows, n_cols, nnz, ld = 3000, 50_000, 40_000, 64
+    dst = torch.from_numpy(rng.integers(0, n_rows // 2, nnz) * 2)            # odd rows have no edges at all
+    src = torch.from_numpy(rng.integers(0, n_cols, nnz))
+    w = torch.from_numpy(rng.random(nnz).astype(np.float32))
+    h = be.build_rect(src.to(DEV), dst.to(DEV), w.to(DEV), n_rows, n_cols)
+    x = torch.randn(n_cols, ld, device=DEV)
+    add = torch.randn(n_rows, ld, device=DEV)
+    y = torch.full((n_rows, ld), float("nan"), device=DEV)
+    ws = be.workspace(h, ld, DEV)
+    be.spmm_ex(h, ld, x, ws, 0, y=y, addend=add, scale=2.0, beta=0.5)
+    want = torch.zeros(n_rows, ld, dtype=torch.float64).index_add_(0, dst, w.double()[:, None] * x.cpu().double()[src])
+    want = 2.0 * want + 0.5 * add.cpu().double()
+    assert not torch.isnan(y).any()
+    assert rel(y.cpu(), want) < 1e-5
+    assert torch.equal(y[1::2], (0.5 * add[1::2]))
+    be.destroy(h)
