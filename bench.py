@@ -282,6 +282,9 @@ def main():
     ap.add_argument("--c5-scale", type=float, default=1.0, help="shrink c5 by this factor (development aid)")
     ap.add_argument("--shard-mode", default="auto", choices=["auto", "bipartite", "rows"],
                     help="N > 1: how the training step is sharded")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1, bipartite sharding: item rows through the peer-memory kernel (lgc_item_exchange) "
+                         "or through ncclAllReduce + lgc_epilogue_apply")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner
@@ -344,8 +347,9 @@ def main():
         # aware sharding (users partitioned, item table replicated, one all-reduce of the item
         # partial sums per layer); "rows" = destination rows partitioned + all-gather per layer
         # (SURVEY.md 8(e)). Both exchange the <= 3*batch loss rows with one small all-reduce.
+        kw = {"exchange": args.exchange} if args.shard_mode != "rows" else {}
         trainer = make_sharded_trainer(ei, ew, g.num_nodes, dim, layers, torch.from_numpy(init),
-                                       mode=args.shard_mode, lr=LR)
+                                       mode=args.shard_mode, lr=LR, **kw)
         shard_kind = type(trainer).__name__
 
         def step(u, p, n):
@@ -416,6 +420,8 @@ def main():
     lib.lgc_profile_read(ms_arr, cnt_arr, n_tags)
     lib.lgc_profile_enable(0)
     if world > 1:
+        if hasattr(trainer, "check_exchange"):
+            trainer.check_exchange()       # a timed-out peer barrier invalidates the run: fail loudly
         trainer.use_graph = True
         launches = lib.lgc_launch_count() - eager0   # graph replays re-run these launches step for step
     light_ms = sum(ms_arr[t] for t in range(0, 4))
@@ -493,8 +499,7 @@ def main():
         # whole step against N x the HBM peak (the collectives add NVLink time on top of it)
         if shard_kind == "BipartiteShardedTrainer":
             comm = 2 * layers * g.n_items * ld * 4 * 2 * (world - 1) // world     # ring all-reduce volume
-            par = (f"users partitioned over {world} GPUs, item table replicated, NCCL all-reduce of the item "
-                   f"partial sums per layer")
+            par = f"users partitioned over {world} GPUs, item table replicated, {exchange_kind(trainer)}"
         else:
             comm = (2 * layers - 1) * trainer.n_cols * ld * 4 * (world - 1) // world
             par = f"destination rows partitioned over {world} GPUs, NCCL all-gather per layer"
@@ -570,7 +575,7 @@ def bench_c5(args, world, rank, dev, lib, pk):
     init_u = torch.from_numpy(np.random.default_rng(4300 + rank).uniform(-bound, bound, (nu, dim)).astype(np.float32))
     init_i = torch.from_numpy(np.random.default_rng(4299).uniform(-bound, bound, (n_items, dim)).astype(np.float32))
     trainer = BipartiteShardedTrainer.from_pairs(user, item, w, part, n_users, n_items, dim, layers, init_u, init_i,
-                                                 lr=LR)
+                                                 lr=LR, exchange=args.exchange)
     ld = padded_dim(dim)
     nnz = 2 * n_edges
 
@@ -671,6 +676,7 @@ def bench_c5(args, world, rank, dev, lib, pk):
     torch.cuda.synchronize()
     launches = (lib.lgc_launch_count() - eager0) * args.steps
     trainer.use_graph = True
+    trainer.check_exchange()
     if rank != 0:
         return finish(world, trainer)
     n_nodes = n_users + n_items
@@ -687,8 +693,7 @@ def bench_c5(args, world, rank, dev, lib, pk):
                    "l2": "inputs (>= 4 GB of tables per rank and step) exceed the 126 MB L2; no flush",
                    "steps_per_epoch": int(n_edges / (BATCH * 40)),
                    "parallelism": f"users partitioned over {world} GPUs (each rank generated and holds only its own "
-                                  f"users' interactions), item table replicated, NCCL all-reduce of the item partial "
-                                  f"sums per layer"},
+                                  f"users' interactions), item table replicated, {exchange_kind(trainer)}"},
         "epoch_s": ms_step * int(n_edges / (BATCH * 40)) * 1e-3,
         "losses_last_step": [float(x) for x in loss3.cpu().tolist()],
         "e2e": {"value": nnz * 2 * layers * args.steps / e2e_s / 1e9, "unit": "GEdges/s",
@@ -704,13 +709,22 @@ def bench_c5(args, world, rank, dev, lib, pk):
     return finish(world, trainer)
 
 
+def exchange_kind(trainer) -> str:
+    if getattr(trainer, "peer", None) is not None:
+        return ("item partial sums reduced, epilogued and broadcast per layer by one peer-memory kernel over NVLink "
+                "(lgc_item_exchange: P2P loads / stores, no NCCL on the item rows)")
+    return "NCCL all-reduce of the item partial sums per layer + replicated epilogue (lgc_epilogue_apply)"
+
+
 def finish(world, trainer):
     """Multi-rank teardown: drop the captured CUDA graph (it holds NCCL work) before the process
     group goes away, then leave without running interpreter-exit destructors in an arbitrary order."""
     if world > 1:
         import torch
         import torch.distributed as dist
-        if hasattr(trainer, "release_graph"):
+        if hasattr(trainer, "close"):
+            trainer.close()
+        elif hasattr(trainer, "release_graph"):
             trainer.release_graph()
         torch.cuda.synchronize()
         dist.barrier()

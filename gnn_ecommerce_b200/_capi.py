@@ -56,6 +56,11 @@ class ScoreTopkArgs(C.Structure):
                 ("workspace", c_vp), ("workspace_bytes", c_sz)]
 
 
+class PeerExchange(C.Structure):
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("bases", c_vp * 8), ("arena_bytes", c_sz), ("ctrl_off", c_sz),
+                ("part", c_vp), ("n_rows", c_i64), ("ld", c_i32), ("timeout_ms", c_i32)]
+
+
 # name -> (restype, argtypes); mirrors include/lgc_b200.h one to one
 _SIGNATURES = {
     "lgc_abi_version": (C.c_int, []),
@@ -94,6 +99,12 @@ _SIGNATURES = {
     "lgc_mark_mapk": (C.c_int, [c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "lgc_score_topk_workspace_bytes": (c_sz, [c_i64, c_i64, C.c_int, C.c_int]),
     "lgc_score_topk": (C.c_int, [C.POINTER(ScoreTopkArgs), c_vp]),
+    "lgc_peer_arena_alloc": (C.c_int, [c_sz, C.POINTER(c_vp), c_vp]),
+    "lgc_peer_arena_open": (C.c_int, [c_vp, C.POINTER(c_vp)]),
+    "lgc_peer_arena_close": (C.c_int, [c_vp]),
+    "lgc_peer_arena_free": (C.c_int, [c_vp]),
+    "lgc_item_exchange": (C.c_int, [C.POINTER(PeerExchange), C.POINTER(SpmmEpilogue), c_vp]),
+    "lgc_peer_exchange_status": (C.c_int, [C.POINTER(PeerExchange), C.POINTER(c_i32), C.POINTER(c_i64)]),
 }
 
 _lib: Optional[C.CDLL] = None

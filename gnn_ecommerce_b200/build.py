@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liblgc_b200.so")
-SOURCES = ["graph.cu", "spmm.cu", "sweep.cu", "rows.cu", "bpr.cu", "train_step.cu", "score.cu", "sampler.cu"]
+SOURCES = ["graph.cu", "spmm.cu", "sweep.cu", "rows.cu", "bpr.cu", "train_step.cu", "score.cu", "sampler.cu", "exchange.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr",
               "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -78,6 +78,93 @@ class RowPartition:
         return torch.cat(parts, 0)
 
 
+# --------------------------------------------------------------------------------- peer memory
+class PeerArena:
+    """One device arena per rank (allocated and exported by liblgc_b200.so as a CUDA IPC handle), mapped
+    into every other rank of `group`: tables carved out of it sit at the same offset on every rank, so
+    `lgc_item_exchange` can load the peers' partial sums and store result rows into every replica over
+    NVLink. The 64-byte handles travel through one all-gather of `torch.distributed`."""
+    ALIGN = 256
+
+    def __init__(self, capi, lib, nbytes: int, device, group=None):
+        self._capi, self._lib, self.device, self.group = capi, lib, torch.device(device), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise RuntimeError("peer arenas support up to 8 ranks")
+        self.nbytes = (int(nbytes) + self.ALIGN - 1) // self.ALIGN * self.ALIGN + 256      # + control block
+        self.ctrl_off = self.nbytes - 256
+        self._top = 0
+        base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            capi.check(lib.lgc_peer_arena_alloc(self.nbytes, C.byref(base), handle), "lgc_peer_arena_alloc")
+        self.base = int(base.value)
+        self.bases, self._opened = [0] * self.world, []
+        self.bases[self.rank] = self.base
+        if self.world > 1:
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().numpy().tobytes()
+            with torch.cuda.device(self.device):
+                for q in range(self.world):
+                    if q == self.rank:
+                        continue
+                    peer = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(every[q * 64:(q + 1) * 64])
+                    capi.check(lib.lgc_peer_arena_open(buf, C.byref(peer)), "lgc_peer_arena_open")
+                    self.bases[q] = int(peer.value)
+                    self._opened.append(int(peer.value))
+
+    def table(self, rows: int, ld: int) -> Tensor:
+        """A zero-filled fp32 `[rows, ld]` table inside the arena (same offset on every rank when every
+        rank asks for the same sequence of tables)."""
+        from .graph import _DeviceArray
+        n = max(int(rows), 1) * int(ld)
+        off = self._top
+        self._top = (off + 4 * n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self._top > self.ctrl_off:
+            raise RuntimeError("peer arena exhausted")
+        t = torch.as_tensor(_DeviceArray(self.base + off, n, "<f4"), device=self.device).view(max(int(rows), 1), int(ld))
+        t._lgc_arena = self                                    # the view must not outlive the arena
+        return t
+
+    @staticmethod
+    def bytes_for(tables: int, rows: int, ld: int) -> int:
+        per = (4 * max(int(rows), 1) * int(ld) + PeerArena.ALIGN - 1) // PeerArena.ALIGN * PeerArena.ALIGN
+        return tables * per
+
+    def descriptor(self, part: Tensor, ld: int, timeout_ms: int = 0):
+        x = self._capi.PeerExchange(world=self.world, rank=self.rank, arena_bytes=self.nbytes, ctrl_off=self.ctrl_off,
+                                    part=part.data_ptr(), n_rows=part.size(0), ld=ld, timeout_ms=timeout_ms)
+        for q, b in enumerate(self.bases):
+            x.bases[q] = b
+        return x
+
+    def status(self) -> Tuple[int, int]:
+        """(error word, exchanges completed) of this rank's control block; synchronises the device."""
+        x = self._capi.PeerExchange(world=self.world, rank=self.rank, arena_bytes=self.nbytes, ctrl_off=self.ctrl_off)
+        for q, b in enumerate(self.bases):
+            x.bases[q] = b
+        err, epoch = C.c_int32(), C.c_int64()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            self._capi.check(self._lib.lgc_peer_exchange_status(C.byref(x), C.byref(err), C.byref(epoch)),
+                             "lgc_peer_exchange_status")
+        return int(err.value), int(epoch.value)
+
+    def close(self) -> None:
+        """Unmap the peers' arenas and free the own one. Collective: every rank must have finished using
+        every arena (the caller synchronises and runs a barrier first)."""
+        if self.base == 0:
+            return
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self._lib.lgc_peer_arena_close(p)
+            self._lib.lgc_peer_arena_free(self.base)
+        self._opened, self.base = [], 0
+
+
 # --------------------------------------------------------------------------------- CUDA backend
 class CudaBackend:
     """The product backend: raw pointers into liblgc_b200.so. No CPU path."""
@@ -148,6 +235,25 @@ class CudaBackend:
         with torch.cuda.device(sums.device):
             rc = self._lib.lgc_epilogue_apply(sums.size(0), ld, _ptr(sums), C.byref(e), _stream())
         self._capi.check(rc, "lgc_epilogue_apply")
+
+    # ---- peer-memory item exchange (csrc/exchange.cu)
+    supports_peer = True
+
+    def peer_arena(self, nbytes: int, device, group) -> "PeerArena":
+        return PeerArena(self._capi, self._lib, nbytes, device, group)
+
+    def item_exchange(self, arena: "PeerArena", part: Tensor, ld: int, mode: int, *, y=None, acc=None, addend=None,
+                      a1=0.0, scale=1.0, beta=0.0, p=None, m=None, v=None, lr=0.0, betas=(0.9, 0.999), eps=1e-8,
+                      step=1, adam_scalars=None, hist=None, ah=None) -> None:
+        """Sum of the ranks' partial item sums + fused epilogue + broadcast of the result rows, one launch
+        per rank over NVLink peer memory (`lgc_item_exchange`); every rank issues the same sequence."""
+        from .graph import _stream
+        e = self._epilogue(mode, y, acc, None, addend, 0.0, a1, scale, beta, p, m, v, lr, betas, eps, step,
+                           adam_scalars, hist, ah)
+        x = arena.descriptor(part, ld)
+        with torch.cuda.device(part.device):
+            rc = self._lib.lgc_item_exchange(C.byref(x), C.byref(e), _stream())
+        self._capi.check(rc, "lgc_item_exchange")
 
     def row_degree(self, handle, n_rows: int, device) -> Tensor:
         """fp32 weighted in-degree of every row of a rect graph, summed in edge-list order (bit-exact
@@ -395,6 +501,18 @@ def bipartite_split(edge_index: Tensor) -> Optional[int]:
     return s if bool((lo_side[0] != lo_side[1]).all()) and s > 0 else None
 
 
+class _PendingItems:
+    """The item rows of one layer, in flight (see `BipartiteShardedTrainer._item_partials`)."""
+
+    def __init__(self, finish):
+        self._finish = finish
+
+    def wait(self) -> None:
+        f, self._finish = self._finish, None
+        if f is not None:
+            f()
+
+
 class BipartiteShardedTrainer(_GraphedStep):
     """Bipartite-aware sharding of the same step (~30x less traffic than the
     all-gather of whole tables): USERS are partitioned over the ranks (balanced by in-degree + 4),
@@ -413,7 +531,7 @@ class BipartiteShardedTrainer(_GraphedStep):
     def __init__(self, edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int, embedding_dim: int,
                  num_layers: int, init_weight: Tensor, n_users: int, lr: float = 0.005, betas=(0.9, 0.999),
                  eps: float = 1e-8, alpha: Optional[Sequence[float]] = None, group=None, backend=None,
-                 ld: Optional[int] = None):
+                 ld: Optional[int] = None, exchange: str = "auto"):
         """From the reference's global edge list (`df_to_graph` layout: [[u; i], [i; u]], every rank passes
         the same one): the first half holds every interaction once, in frame order."""
         n_users = int(n_users)
@@ -430,7 +548,8 @@ class BipartiteShardedTrainer(_GraphedStep):
         lo, hi = part.lo(rank), part.hi(rank)
         mine = (user >= lo) & (user < hi)                                    # keeps frame order
         self._setup(user[mine], item[mine], w[mine].float(), part, n_users, int(num_nodes) - n_users, embedding_dim,
-                    num_layers, init_weight[lo:hi], init_weight[n_users:], lr, betas, eps, alpha, group, backend, ld)
+                    num_layers, init_weight[lo:hi], init_weight[n_users:], lr, betas, eps, alpha, group, backend, ld,
+                    exchange)
 
     @staticmethod
     def _pairs_layout_ok(edge_index: Tensor, n_users: int) -> bool:
@@ -443,17 +562,18 @@ class BipartiteShardedTrainer(_GraphedStep):
     @classmethod
     def from_pairs(cls, user: Tensor, item: Tensor, weight: Tensor, part: RowPartition, n_users: int, n_items: int,
                    embedding_dim: int, num_layers: int, init_users: Tensor, init_items: Tensor, lr: float = 0.005,
-                   betas=(0.9, 0.999), eps: float = 1e-8, alpha=None, group=None, backend=None, ld=None):
+                   betas=(0.9, 0.999), eps: float = 1e-8, alpha=None, group=None, backend=None, ld=None,
+                   exchange: str = "auto"):
         """From this rank's OWN interactions only: `user` (global user ids inside the rank's range of
         `part`), `item` (un-offset item ids), `weight`; `init_users` = the rank's rows of the initial
         table, `init_items` = all item rows (replicated)."""
         self = cls.__new__(cls)
         self._setup(user, item, weight.float(), part, n_users, n_items, embedding_dim, num_layers, init_users,
-                    init_items, lr, betas, eps, alpha, group, backend, ld)
+                    init_items, lr, betas, eps, alpha, group, backend, ld, exchange)
         return self
 
     def _setup(self, user, item, w, part, n_users, n_items, embedding_dim, num_layers, init_users, init_items, lr,
-               betas, eps, alpha, group, backend, ld):
+               betas, eps, alpha, group, backend, ld, exchange="auto"):
         assert num_layers >= 1
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -500,17 +620,73 @@ class BipartiteShardedTrainer(_GraphedStep):
 
         def table(rows):
             return torch.zeros(max(rows, 1), ld, dtype=torch.float32, device=self.dev)
+        n_x = max(self.layers - 1, 2)                           # stored layers (forward), ping-pong (backward)
+        # ---- item-row exchange: one kernel over NVLink peer memory (`lgc_item_exchange`) when the backend
+        # has it, else ncclAllReduce + `lgc_epilogue_apply`. Every item table an epilogue writes and the
+        # partial-sum tables then live in the rank's peer arena, at the same offsets on every rank.
+        self.peer = self._open_peer_arena(exchange, PeerArena.bytes_for(6 + n_x, ni, ld))
+        itable = self.peer.table if self.peer is not None else (lambda rows, ld_: table(rows))
         self.e0_u, self.m_u, self.v_u = table(nu), table(nu), table(nu)
-        self.e0_i, self.m_i, self.v_i = table(ni), table(ni), table(ni)
+        self.e0_i, self.m_i, self.v_i = itable(ni, ld), itable(ni, ld), itable(ni, ld)
         self.e0_u[: self.n_local, : self.dim] = init_users.to(self.dev)
         self.e0_i[:, : self.dim] = init_items.to(self.dev)
-        self.out_u, self.out_i = table(nu), table(ni)
-        n_x = max(self.layers - 1, 2)                           # stored layers (forward), ping-pong (backward)
-        self.xu, self.xi = [table(nu) for _ in range(n_x)], [table(ni) for _ in range(n_x)]
-        self.part_i = [table(ni), table(ni)]                    # partial item sums in flight (two layers)
+        self.out_u, self.out_i = table(nu), itable(ni, ld)
+        self.xu, self.xi = [table(nu) for _ in range(n_x)], [itable(ni, ld) for _ in range(n_x)]
+        self.part_i = [itable(ni, ld), itable(ni, ld)]          # partial item sums in flight (two layers)
         self.g_u, self.z_u, self.g_i, self.z_i = table(nu), table(nu), table(ni), table(ni)
         self.n_cols = self.n_items                              # rows exchanged per layer
+        self._side = torch.cuda.Stream(self.dev) if self.peer is not None else None
+        if self.peer is not None:
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)                      # every arena is initialised before any peer writes
         self._init_graph_state()
+
+    def _open_peer_arena(self, exchange: str, nbytes: int):
+        """"peer": required; "nccl": never; "auto": when the backend has it, 2..8 ranks, and every rank
+        could map every arena (else all ranks fall back to NCCL together). LGC_EXCHANGE overrides "auto"."""
+        import os
+        if exchange == "auto":
+            exchange = os.environ.get("LGC_EXCHANGE", "auto")
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        able = (exchange != "nccl" and self.world > 1 and self.world <= 8 and self.dev.type == "cuda"
+                and bool(getattr(self.backend, "supports_peer", False)))
+        if not able:
+            if exchange == "peer":
+                raise RuntimeError("exchange='peer' needs 2..8 CUDA ranks and a backend with lgc_item_exchange")
+            return None
+        arena, err = None, None
+        try:
+            arena = self.backend.peer_arena(nbytes, self.dev, self.group)
+        except Exception as e:                                   # noqa: BLE001 - reported below, collectively
+            err = e
+        ok = torch.tensor([0 if arena is None else 1], device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            return arena
+        if arena is not None:
+            arena.close()
+        if exchange == "peer":
+            raise RuntimeError(f"peer arenas could not be mapped on every rank: {err}")
+        import warnings
+        warnings.warn(f"lgc_item_exchange unavailable ({err}); item rows go through ncclAllReduce")
+        return None
+
+    def check_exchange(self) -> None:
+        """Raises if a barrier of the peer-memory exchange timed out (synchronises the device)."""
+        if self.peer is not None:
+            err, _ = self.peer.status()
+            if err:
+                raise RuntimeError(f"lgc_item_exchange: a peer did not arrive in time (phase {err}); results invalid")
+
+    def close(self) -> None:
+        """Collective teardown of the peer arenas (call on every rank before destroying the process group)."""
+        self.release_graph()
+        if getattr(self, "peer", None) is not None:
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)
+            self.peer.close()
+            self.peer = None
 
     def __del__(self):
         for name in ("gu", "gi"):
@@ -526,13 +702,29 @@ class BipartiteShardedTrainer(_GraphedStep):
         if self.world > 1:
             dist.all_reduce(t, group=self.group)
 
-    def _item_partials(self, x_u: Tensor, out: Tensor):
-        """out = this rank's partial sums of (A_hat x)[items] over its own users, then the ASYNCHRONOUS
-        all-reduce of the partials; the caller waits on the returned handle only when it needs the item
-        rows, so the NVLink exchange hides behind the kernels issued in between."""
-        self.backend.spmm_ex(self.gi, self.ld, x_u, self.ws_i, 0, y=out, scale=1.0)
-        work = dist.all_reduce(out, group=self.group, async_op=True) if self.world > 1 else None
-        return work
+    def _item_partials(self, x_u: Tensor, part: Tensor, mode: int, **epi) -> "_PendingItems":
+        """part = this rank's partial sums of (A_hat x)[items] over its own users, then -- ASYNCHRONOUSLY --
+        their sum over the ranks and the item rows' epilogue `mode` (0 PLAIN into epi['y'], 3 ADAM, 4
+        FWD_FINAL). The caller waits on the returned object only when it needs the item rows, so the NVLink
+        exchange hides behind the kernels issued in between. Peer mode: one `lgc_item_exchange` launch on a
+        side stream does all of it; NCCL mode: async all-reduce, epilogue on the main stream at wait()."""
+        b = self.backend
+        b.spmm_ex(self.gi, self.ld, x_u, self.ws_i, 0, y=part, scale=1.0)
+        if self.peer is not None:
+            main = torch.cuda.current_stream(self.dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                b.item_exchange(self.peer, part, self.ld, mode, **epi)
+            return _PendingItems(lambda: main.wait_stream(self._side))
+        work = dist.all_reduce(part, group=self.group, async_op=True) if self.world > 1 else None
+        plain_in_place = mode == 0 and epi.get("y") is part     # forward layers < K: the sums ARE x_l
+
+        def finish():
+            if work is not None:
+                work.wait()
+            if not plain_in_place:
+                b.epilogue_apply(part, self.ld, mode, **epi)
+        return _PendingItems(finish)
 
     # ------------------------------------------------------------------ forward only
     def propagate(self) -> Tuple[Tensor, Tensor]:
@@ -540,9 +732,16 @@ class BipartiteShardedTrainer(_GraphedStep):
         Layers 1..K-1 store x_l; layer K folds the whole mean into its epilogue (FWD_FINAL), for the
         user rows inside the SpMM, for the item rows in one `lgc_epilogue_apply` after the all-reduce."""
         b, a, K, ld = self.backend, self.alpha, self.layers, self.ld
-        hist_u, hist_i = [self.e0_u], [self.e0_i]
+        hist_u = [self.e0_u]
+        hist_i = [self.e0_i] + self.xi[: K - 1]                 # layer tables of the items, in layer order
+
+        def items_of_layer(l: int, x_u: Tensor) -> "_PendingItems":
+            if l < K:                                           # x_l of the items, summed in place
+                return self._item_partials(x_u, self.xi[l - 1], 0, y=self.xi[l - 1], scale=1.0)
+            return self._item_partials(x_u, self.part_i[0], 4, acc=self.out_i, a1=a[K], hist=hist_i, ah=a[:K])
+
         ci = self.e0_i
-        work = self._item_partials(self.e0_u, self.xi[0] if K > 1 else self.part_i[0])
+        pend = items_of_layer(1, self.e0_u)
         for l in range(1, K + 1):
             last = l == K
             # user rows of layer l from the item rows of layer l-1
@@ -551,18 +750,13 @@ class BipartiteShardedTrainer(_GraphedStep):
             else:
                 b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=self.xu[l - 1], scale=1.0)
             # item partials of layer l+1 need only the user rows of layer l: issued BEFORE waiting for the
-            # all-reduce of layer l, which therefore overlaps both kernels
-            nwork = None
+            # exchange of layer l, which therefore overlaps both kernels
+            npend = None if last else items_of_layer(l + 1, self.xu[l - 1])
+            pend.wait()
             if not last:
-                nwork = self._item_partials(self.xu[l - 1], self.xi[l] if l + 1 < K else self.part_i[0])
-            if work is not None:
-                work.wait()
-            if last:
-                b.epilogue_apply(self.part_i[0], ld, 4, acc=self.out_i, a1=a[K], hist=hist_i, ah=a[:K])
-            else:
-                ci = self.xi[l - 1]                             # all-reduced in place: x_l of the items
-                hist_u.append(self.xu[l - 1]); hist_i.append(ci)
-                work = nwork
+                ci = self.xi[l - 1]                             # x_l of the items
+                hist_u.append(self.xu[l - 1])
+                pend = npend
         return self.out_u, self.out_i
 
     # ------------------------------------------------------------------ one mini-batch
@@ -588,24 +782,26 @@ class BipartiteShardedTrainer(_GraphedStep):
 
         # ---- backward (Horner on the symmetric operator) + Adam: h_l = alpha_l G + A h_{l+1}
         adam = dict(lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, **self._adam_kw())
-        cu, ci, scale = self.g_u, self.g_i, a[K]
-        work = self._item_partials(cu, self.part_i[0])
-        for l in range(K - 1, -1, -1):
-            pi = self.part_i[(K - 1 - l) & 1]
+        def items_bwd(l: int, x_u: Tensor, scale: float) -> "_PendingItems":
+            part = self.part_i[(K - 1 - l) & 1]
             if l > 0:
-                nu_, ni_ = self.xu[l & 1], self.xi[l & 1]
+                return self._item_partials(x_u, part, 0, y=self.xi[l & 1], addend=self.g_i, scale=scale, beta=a[l])
+            return self._item_partials(x_u, part, 3, addend=self.z_i, scale=scale, p=self.e0_i, m=self.m_i,
+                                       v=self.v_i, **adam)
+
+        ci, scale = self.g_i, a[K]
+        pend = items_bwd(K - 1, self.g_u, scale)
+        for l in range(K - 1, -1, -1):
+            if l > 0:
+                nu_ = self.xu[l & 1]
                 b.spmm_ex(self.gu, ld, ci, self.ws_u, 0, y=nu_, addend=self.g_u, scale=scale, beta=a[l])
-                nwork = self._item_partials(nu_, self.part_i[(K - l) & 1])      # item partials of the next layer
-                if work is not None:
-                    work.wait()
-                b.epilogue_apply(pi, ld, 0, y=ni_, addend=self.g_i, scale=scale, beta=a[l])
-                cu, ci, scale, work = nu_, ni_, 1.0, nwork
+                npend = items_bwd(l - 1, nu_, 1.0)              # item partials of the next layer
+                pend.wait()
+                ci, scale, pend = self.xi[l & 1], 1.0, npend
             else:
                 b.spmm_ex(self.gu, ld, ci, self.ws_u, 3, addend=self.z_u, scale=scale, p=self.e0_u, m=self.m_u,
                           v=self.v_u, **adam)
-                if work is not None:
-                    work.wait()
-                b.epilogue_apply(pi, ld, 3, addend=self.z_i, scale=scale, p=self.e0_i, m=self.m_i, v=self.v_i, **adam)
+                pend.wait()
         self.g_u.index_fill_(0, locc, 0.0)
         self.z_u.index_fill_(0, locc, 0.0)
         self.g_i.index_fill_(0, items, 0.0)

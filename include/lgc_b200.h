@@ -314,6 +314,45 @@ int lgc_score_topk(const lgc_score_topk_args* args, void* stream);
 int lgc_mark_mapk(int64_t n_users, int k, const int64_t* topk_items, const int64_t* held_ptr,
                   const int64_t* held_items, float* per_user, double* out2, void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU item-row exchange over peer memory
+ * (SURVEY.md 8(b) last bullet / 8(e): the communicating variant of the LGConv layer; the reference
+ * itself is single-device, src/train_lightgcn.py:35-37.) In the bipartite-sharded step every rank holds
+ * PARTIAL sums of (A_hat x)[items] over its own users; lgc_item_exchange completes the aggregate of
+ * PyG's LGConv (call site src/lightgcn.py:96) for the item rows and applies the fused epilogue in ONE
+ * kernel over NVLink peer memory -- reduce-scatter by P2P loads in fixed rank order (deterministic),
+ * epilogue on the owned slice, all-gather by P2P stores -- instead of ncclAllReduce followed by
+ * lgc_epilogue_apply. Every rank must issue the same sequence of lgc_item_exchange calls.
+ *
+ * Memory: one ARENA per rank, allocated by this library (cudaMalloc, zero-filled) and exported as a
+ * CUDA IPC handle (LGC_PEER_HANDLE_BYTES host bytes the caller passes to the other ranks however it
+ * likes -- the Python driver all-gathers them over torch.distributed). lgc_peer_arena_open maps a
+ * peer's arena into this process. The partial-sum table and every table the epilogue WRITES
+ * (PLAIN: y; ADAM: p, m, v; FWD_FINAL: acc) must lie inside the arena at the same offset on every
+ * rank; operands that are only read (addend, hist, adam_scalars) are local and may live anywhere. A
+ * LGC_PEER_CTRL_BYTES control block inside the arena (zero at start, 256-byte aligned offset) carries
+ * the barrier tickets; they are counted on the device, so a captured CUDA graph may replay the call.
+ * Waits are bounded by timeout_ms (0: ~20 s): a timeout sets the error word read by
+ * lgc_peer_exchange_status (synchronous) instead of hanging the GPU. */
+#define LGC_PEER_MAX 8
+#define LGC_PEER_HANDLE_BYTES 64
+#define LGC_PEER_CTRL_BYTES 256
+int lgc_peer_arena_alloc(size_t bytes, void** d_base, void* h_handle);
+int lgc_peer_arena_open(const void* h_handle, void** d_peer_base);
+int lgc_peer_arena_close(void* d_peer_base);
+int lgc_peer_arena_free(void* d_base);
+typedef struct {
+  int32_t world, rank;
+  void* bases[LGC_PEER_MAX];   /* arena of every rank as mapped in THIS process (bases[rank]: own)   */
+  size_t arena_bytes;
+  size_t ctrl_off;             /* byte offset of the control block inside every arena               */
+  const float* part;           /* [n_rows, ld] partial sums inside the own arena                    */
+  int64_t n_rows;              /* rank r reduces rows [r * ceil(n_rows / world), ...)               */
+  int32_t ld;
+  int32_t timeout_ms;
+} lgc_peer_exchange;
+int lgc_item_exchange(const lgc_peer_exchange* x, const lgc_spmm_epilogue* epilogue, void* stream);
+int lgc_peer_exchange_status(const lgc_peer_exchange* x, int32_t* h_error, int64_t* h_epoch);
+
 /* Diagnostics: clock64() cycles per phase of the light-row SpMM kernel since the last call, summed
  * over warps (only when the process runs with LGC_LIGHT_PHASES=1; zeros otherwise). out8[0..4] =
  * wait for CSR slices | gathers | wait for operand tiles | epilogue | store + refill; out8[5] =

@@ -41,18 +41,38 @@ def _worker(rank, world, port, mode, dim, layers, out_dir):
     ew = torch.from_numpy(g.edge_weight()).to(dev)
     torch.manual_seed(3)
     init = torch.nn.init.xavier_uniform_(torch.empty(g.num_nodes, dim))
-    tr = make_sharded_trainer(ei, ew, g.num_nodes, dim, layers, init, mode=mode, lr=LR)
     pl = synth.purchase_lists(g)
-    rng = np.random.default_rng(9)
-    losses = []
-    for _ in range(5):                       # 2 eager steps, 1 capture, 2 CUDA-graph replays
-        u, p, n = (torch.from_numpy(x).to(dev) for x in synth.sample_triples(pl, 256, g.n_users, g.n_items, rng))
-        losses.append(tr.step(u, p, n, DECAY).cpu().numpy())
-    w, emb = tr.weight().cpu().numpy(), tr.embedding().cpu().numpy()
+    results = {}
+    # bipartite: the item rows go through the peer-memory kernel (lgc_item_exchange) AND, as a second
+    # trainer, through ncclAllReduce + lgc_epilogue_apply; with two ranks a + b has one rounding, so the
+    # two must agree bit for bit
+    for exch in (("nccl", "peer") if mode == "bipartite" else (None,)):
+        kw = {"exchange": exch} if exch else {}
+        tr = make_sharded_trainer(ei, ew, g.num_nodes, dim, layers, init, mode=mode, lr=LR, **kw)
+        if exch == "peer":
+            assert tr.peer is not None and tr.peer.world == world
+        rng = np.random.default_rng(9)
+        losses = []
+        for _ in range(5):                       # 2 eager steps, 1 capture, 2 CUDA-graph replays
+            u, p, n = (torch.from_numpy(x).to(dev) for x in synth.sample_triples(pl, 256, g.n_users, g.n_items, rng))
+            losses.append(tr.step(u, p, n, DECAY).cpu().numpy())
+        w, emb = tr.weight().cpu().numpy(), tr.embedding().cpu().numpy()
+        if hasattr(tr, "check_exchange"):
+            tr.check_exchange()
+            if exch == "peer":
+                assert tr.peer.status()[1] == 5 * 2 * layers + layers      # 5 steps + the embedding() call
+        results[exch] = (np.array(losses), w, emb)
+        if hasattr(tr, "close"):
+            tr.close()
+        elif hasattr(tr, "release_graph"):
+            tr.release_graph()
+        del tr
+    if mode == "bipartite":
+        for a, b in zip(results["nccl"], results["peer"]):
+            assert np.array_equal(a, b), "peer-memory exchange differs from ncclAllReduce + epilogue"
+    losses, w, emb = results["peer" if mode == "bipartite" else None]
     if rank == 0:
-        np.savez(os.path.join(out_dir, f"{mode}.npz"), losses=np.array(losses), w=w, emb=emb)
-    if hasattr(tr, "release_graph"):
-        tr.release_graph()
+        np.savez(os.path.join(out_dir, f"{mode}.npz"), losses=losses, w=w, emb=emb)
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
