@@ -456,6 +456,7 @@ def main():
     light_avg_ms = light_ms / max(light_cnt, 1)
     class_ms = {"light": light_ms / args.steps, "heavy": heavy_ms / args.steps, "finish": finish_ms / args.steps,
                 "bpr": ms_arr[12] / args.steps,
+                "item_exchange": [round(ms_arr[14] / args.steps, 4), cnt_arr[14] // args.steps],   # incl. waiting for peers
                 # per epilogue mode {plain, fwd-init, fwd-rmw (+ fwd-final), adam}: ms per step / launches per step
                 "rows_by_mode": [[round(ms_arr[t] / args.steps, 4), cnt_arr[t] // args.steps] for t in range(0, 4)],
                 "sweep_by_mode": [[round(ms_arr[t] / args.steps, 4), cnt_arr[t] // args.steps] for t in range(4, 8)]}

@@ -44,6 +44,7 @@ enum ProfTag : int {
   PROF_FINISH = 8,   // + EpiMode
   PROF_BPR = 12,
   PROF_MISC = 13,
+  PROF_EXCHANGE = 14,   // lgc_item_exchange (includes the wait for the slowest rank)
   PROF_SCORE_CONVERT = 16,
   PROF_SCORE_GEMM = 17,
   PROF_SCORE_SELECT = 18,

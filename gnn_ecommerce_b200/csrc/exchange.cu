@@ -20,12 +20,14 @@
 //   B  rank r owns the float4 range [v_beg, v_end) of the table: it loads that range from ALL
 //      arenas (P2P loads over NVLink, fixed rank order 0..world-1: deterministic), applies the
 //      epilogue with the replicated local operands and stores the results into EVERY arena
-//      (P2P stores): all replicas stay bit-identical because one rank computes each element;
+//      (P2P stores): all replicas stay bit-identical because one rank computes each element. ADAM
+//      sends only the new weights; the moments m, v of a row stay with the rank that owns the row;
 //   C  the last block of the rank to finish publishes "my stores are performed" and waits for the
 //      same ticket of every peer; the kernel ends when every arena holds every slice.
 // Tickets are monotone (2 per launch, counted in the control block, so a captured CUDA graph can
 // replay the launch) and every wait is bounded: a timeout raises the error word of the control block
 // instead of hanging the GPU (read by lgc_peer_exchange_status).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -122,7 +124,6 @@ __device__ __forceinline__ void epi_values(const EpiArgs& a, const float (&s)[4]
 template <int MODE, int WMAX, int U>
 __global__ void __launch_bounds__(256, 2)
 k_item_exchange(XArgs x, EpiArgs a) {
-  constexpr int N_OUT = MODE == EPI_ADAM ? 3 : 1;
   PeerCtrl* my = reinterpret_cast<PeerCtrl*>(x.base[x.rank] + x.ctrl_off);
   __shared__ unsigned int s_ticket;
   __shared__ int s_last;
@@ -175,10 +176,11 @@ k_item_exchange(XArgs x, EpiArgs a) {
         epi_values<MODE>(a, s, pre[u], out);
 #pragma unroll
         for (int q = 0; q < WMAX; ++q)
-          if (q < x.world) {
-#pragma unroll
-            for (int o = 0; o < N_OUT; ++o) st_peer(reinterpret_cast<float*>(x.base[q] + x.out_off[o]) + off, out[o]);
-          }
+          if (q < x.world) st_peer(reinterpret_cast<float*>(x.base[q] + x.out_off[0]) + off, out[0]);
+        if constexpr (MODE == EPI_ADAM) {      // the moments of a row are only ever read by the rank that owns it
+          stv_stream<4>(a.m + off, out[1]);
+          stv_stream<4>(a.v + off, out[2]);
+        }
       }
     }
   }
@@ -279,7 +281,7 @@ extern "C" int lgc_item_exchange(const lgc_peer_exchange* px, const lgc_spmm_epi
     case LGC_EPI_ADAM:
       LGC_REQUIRE(e->addend && e->p && e->m && e->v && (e->step >= 1 || e->adam_scalars),
                   "ADAM needs addend, p, m, v and step >= 1 (or device scalars)");
-      outs[0] = e->p; outs[1] = e->m; outs[2] = e->v; n_out = 3;
+      outs[0] = e->p;                     // m, v: local stores (rows this rank owns)
       a.p = e->p; a.m = e->m; a.v = e->v;
       if (e->adam_scalars) a.adam_dev = reinterpret_cast<const AdamScalars*>(e->adam_scalars);
       else a.adam = make_adam_scalars(e->lr, e->beta1, e->beta2, e->eps, e->step);
@@ -312,11 +314,14 @@ extern "C" int lgc_item_exchange(const lgc_peer_exchange* px, const lgc_spmm_epi
   const int64_t n_vec = x.v_end - x.v_beg;
   cudaStream_t st = (cudaStream_t)stream;
   NvtxRange nvtx("lgc_item_exchange");
-  // up to two CTAs per SM (the launch overlaps the rows kernel of the same layer and spins in phase A
-  // until the slowest rank arrives); U * world loads in flight per thread
+  ProfScope ps(PROF_EXCHANGE, st);
+  // at most one CTA per SM: the launch overlaps the rows kernel of the same layer and spins in phase A
+  // until the slowest rank arrives, so it must leave most of every SM to that kernel; U * world loads in
+  // flight per thread (LGC_XCHG_CTAS: development override of the CTA cap)
+  static const int cta_cap = [] { const char* e = getenv("LGC_XCHG_CTAS"); return e ? std::max(1, atoi(e)) : 0; }();
 #define LGC_XCASE(WMAX, U)                                                                                     \
   {                                                                                                            \
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_vec, 256 * (U)), 2 * device_sm_count())); \
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_vec, 256 * (U)), cta_cap ? cta_cap : device_sm_count())); \
     switch (e->mode) {                                                                                         \
       case LGC_EPI_PLAIN: k_item_exchange<EPI_PLAIN, WMAX, U><<<grid, 256, 0, st>>>(x, a); break;              \
       case LGC_EPI_ADAM: k_item_exchange<EPI_ADAM, WMAX, U><<<grid, 256, 0, st>>>(x, a); break;                \

@@ -466,17 +466,32 @@ __device__ __forceinline__ unsigned short bits_of(unsigned key) {
 // two keys per 32-bit word. T'_u = that value: at least r tiles hold an item whose true score is
 // >= T'_u, at most n_seen of them through a seen item, so the k-th best MASKED score is >= T'_u.
 // Small item sets (few tiles) select among the 16-item groups instead: their stored upper bounds
-// are turned back into lower bounds (U - 2^-10 |U| - 2 e).
+// are turned back into lower bounds (U - 2^-10 |U| - 2 e). Very large item sets (more tiles than keys
+// fit in shared memory: > 409 600 items) select among the maxima of `fold` consecutive tiles: every
+// such maximum still stands for a distinct item, so the r-th largest is a valid (slightly lower) T'_u.
 __global__ void __launch_bounds__(256)
 k_threshold(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, int use_groups, int n_tiles,
-            int pitch, int u_pad, int n_users, int64_t user0, int k, const int64_t* __restrict__ seen_ptr,
+            int fold, int pitch, int u_pad, int n_users, int64_t user0, int k, const int64_t* __restrict__ seen_ptr,
             const float* __restrict__ anorm, const float* __restrict__ btile, ScoreScalars* sc, float out_scale,
             float eps_abs, float* __restrict__ thr_grp, float* __restrict__ thr_exact, uint8_t* __restrict__ flag,
             int32_t* __restrict__ fb_users) {
   extern __shared__ unsigned short s_keys[];   // [32][pitch]
   const int u0 = blockIdx.x * 32;
-  const int n_sel = use_groups ? n_tiles * 8 : n_tiles;
-  for (int i0 = threadIdx.x; i0 < pitch * 32; i0 += 1024) {
+  const int n_sel = use_groups ? n_tiles * 8 : (n_tiles + fold - 1) / fold;
+  if (fold > 1) {
+    for (int i = threadIdx.x; i < pitch * 32; i += 256) {
+      const int t = i >> 5, j = i & 31;
+      unsigned key = 0;                              // padding: below every real key
+      if (t < n_sel) {
+        const int t_end = min(n_tiles, (t + 1) * fold);
+        for (int tt = t * fold; tt < t_end; ++tt)
+          key = max(key, key_of((unsigned short)(gtile[(size_t)tt * u_pad + u0 + j] & 0xFFFFu)));
+        if (key == 0) key = 1;
+      }
+      s_keys[j * pitch + t] = (unsigned short)key;
+    }
+  }
+  for (int i0 = threadIdx.x; fold == 1 && i0 < pitch * 32; i0 += 1024) {
     uint32_t raw[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {                 // four loads in flight per thread
@@ -1257,15 +1272,17 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
   }
 
   const int use_groups = L.n_tiles < 256 ? 1 : 0;
-  const int n_sel = L.n_tiles * (use_groups ? 8 : 1);
+  // keys per user in k_threshold's shared memory: at most 3 200 (200 KB for 32 users); beyond 409 600 items
+  // the threshold is selected among the maxima of `fold` consecutive tiles (LGC_SCORE_FOLD: test override)
+  const char* fold_env = getenv("LGC_SCORE_FOLD");
+  int fold = use_groups ? 1 : (int)ceil_div(L.n_tiles, 3200);
+  if (fold_env && !use_groups) fold = std::max(fold, std::min(atoi(fold_env), std::max(1, L.n_tiles / 64)));
+  const int n_sel = use_groups ? L.n_tiles * 8 : (int)ceil_div(L.n_tiles, fold);
   int pitch = (n_sel + 1) / 2 * 2;                 // keys per user row: even, with an odd word count
   if ((pitch / 2) % 2 == 0) pitch += 2;
   const size_t thr_smem = (size_t)pitch * 32 * 2;
   const float eps_abs = (float)L.kp * 0.001953125f;   // subnormal fp16 inputs: kp * 2^-9 (scaled units)
-  if (thr_smem > 200 * 1024) {
-    set_error("lgc_score_topk: n_items above 409600 is not supported yet");
-    return LGC_ERR_UNSUPPORTED;
-  }
+  LGC_REQUIRE(thr_smem <= 200 * 1024, "lgc_score_topk: threshold keys do not fit shared memory");
   const int d4 = (a->d + 3) / 4;
   const size_t rs_smem = (size_t)128 * (d4 + 1) * 16 + (size_t)8 * kRowsPerWarp * d4 * 16;
   const size_t ex_smem = (size_t)d4 * 16;
@@ -1300,7 +1317,7 @@ extern "C" int lgc_score_topk(const lgc_score_topk_args* a, void* stream) {
     if (dbg_mode) continue;          // timing experiments: GEMM only, outputs are not valid
     {
       ProfScope ps(PROF_SCORE_SELECT, st);
-      k_threshold<<<nu_pad / 32, 256, thr_smem, st>>>(g128, g16, use_groups, L.n_tiles, pitch, L.chunk_pad, nu, user0,
+      k_threshold<<<nu_pad / 32, 256, thr_smem, st>>>(g128, g16, use_groups, L.n_tiles, fold, pitch, L.chunk_pad, nu, user0,
                                                      a->k, a->seen_ptr, anorm, btile, sc, out_scale, eps_abs, thr_grp,
                                                      thr_exact, flag, fb);
       LGC_LAUNCH_CHECK();

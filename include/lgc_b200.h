@@ -52,7 +52,7 @@ int lgc_ld_supported(int ld);
 /* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional
  * per-kernel-class timing with CUDA events recorded on the launching stream around each launch.
  * Tags: 0-3 light-row SpMM by epilogue {plain, fwd-init, fwd-rmw, adam}, 4-7 heavy-row SpMM,
- * 8-11 split-row finish, 12 BPR, 13 misc, 16-22 scoring {convert, gemm, threshold, rescore,
+ * 8-11 split-row finish, 12 BPR, 13 misc, 14 peer-memory item exchange, 16-22 scoring {convert, gemm, threshold, rescore,
  * select, exhaustive, scan}.
  * lgc_profile_read synchronises the recorded events, sums milliseconds and launch counts per tag
  * into the HOST arrays and clears the record. */
@@ -328,7 +328,9 @@ int lgc_mark_mapk(int64_t n_users, int k, const int64_t* topk_items, const int64
  * likes -- the Python driver all-gathers them over torch.distributed). lgc_peer_arena_open maps a
  * peer's arena into this process. The partial-sum table and every table the epilogue WRITES
  * (PLAIN: y; ADAM: p, m, v; FWD_FINAL: acc) must lie inside the arena at the same offset on every
- * rank; operands that are only read (addend, hist, adam_scalars) are local and may live anywhere. A
+ * rank; operands that are only read (addend, hist, adam_scalars) are local and may live anywhere.
+ * ADAM stores the new weights p into every arena; the moments m, v of a row are only updated on the
+ * rank that owns the row (rank r: rows [r * ceil(n_rows / world), ...)) -- they are sharded, not replicated. A
  * LGC_PEER_CTRL_BYTES control block inside the arena (zero at start, 256-byte aligned offset) carries
  * the barrier tickets; they are counted on the device, so a captured CUDA graph may replay the call.
  * Waits are bounded by timeout_ms (0: ~20 s): a timeout sets the error word read by

@@ -77,6 +77,34 @@ def test_topk_matches_oracle(n_users, n_items, dim, k):
     assert stats[1] > 0
 
 
+def test_topk_with_folded_threshold_keys(monkeypatch):
+    """Item sets above 409 600 select the per-user threshold among maxima of `fold` consecutive tiles
+    (the keys of more tiles do not fit k_threshold's shared memory). LGC_SCORE_FOLD forces the same code
+    path at a size the dense oracle handles quickly; the result must stay exact."""
+    monkeypatch.setenv("LGC_SCORE_FOLD", "3")
+    rng = np.random.default_rng(77)
+    n_users, n_items, dim, k = 600, 40_000, 64, 20
+    ue = (rng.standard_normal((n_users, dim)) * 0.05).astype(np.float32)
+    ie = (rng.standard_normal((n_items, dim)) * rng.uniform(0.01, 0.2, (n_items, 1))).astype(np.float32)
+    ptr, items = _random_seen(rng, n_users, n_items, heavy=[(5, 40)])
+    top, sc, stats = _run(ue, ie, None, ptr, items, k)
+    assert _check_topk(ue, ie, np.arange(n_users), ptr, items, k, top, sc) > 0.98
+    assert stats[0] <= 2 and stats[1] > 0
+
+
+def test_topk_beyond_409600_items():
+    """c5-sized item set (500 K items in BASELINE.json config 5): 450 K items x a few users against the
+    dense fp32 oracle."""
+    rng = np.random.default_rng(450)
+    n_users, n_items, dim, k = 160, 450_000, 64, 20
+    ue = (rng.standard_normal((n_users, dim)) * 0.05).astype(np.float32)
+    ie = (rng.standard_normal((n_items, dim)) * rng.uniform(0.01, 0.2, (n_items, 1))).astype(np.float32)
+    ptr, items = _random_seen(rng, n_users, n_items)
+    top, sc, stats = _run(ue, ie, None, ptr, items, k)
+    assert _check_topk(ue, ie, np.arange(n_users), ptr, items, k, top, sc) > 0.98
+    assert stats[0] <= 2 and stats[1] > 0
+
+
 def test_topk_user_subset_and_padded_tables():
     """`user_id_list` semantics (gather, arbitrary order, repeats) on padded [N, ld] tables."""
     rng = np.random.default_rng(11)
