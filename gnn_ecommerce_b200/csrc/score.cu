@@ -598,6 +598,10 @@ __device__ __forceinline__ float4 load_row_f4(const float* __restrict__ row, int
 // in detail (its four group words) only when its own upper bound reaches the user's threshold.
 // Entries that do not fit `list_cap` are dropped and their user is sent to the exhaustive path.
 // Four users per thread are in flight at once (the loop is latency-bound otherwise).
+#ifndef LGC_SCAN_UPT
+#define LGC_SCAN_UPT 4
+#endif
+constexpr int kScanUPT = LGC_SCAN_UPT;       // users per thread in flight
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, int u_pad, int n_users,
@@ -605,7 +609,7 @@ k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, 
        int* __restrict__ grp_cur, int* __restrict__ list, int list_cap, uint8_t* __restrict__ flag,
        uint8_t* __restrict__ hitmask) {
   const int tile = blockIdx.x;
-  const int per = round_up((n_users + gridDim.y - 1) / gridDim.y, 1024);
+  const int per = round_up((n_users + gridDim.y - 1) / gridDim.y, 256 * kScanUPT);
   const int u_beg = blockIdx.y * per, u_end = min(n_users, u_beg + per);
   __shared__ int s_cnt[8];
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
@@ -613,15 +617,15 @@ k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, 
   int my[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (FILL) {
     // second pass: the count pass left one byte per (tile, user) with the hit groups
-    for (int u0 = u_beg; u0 < u_end; u0 += 1024) {
-      unsigned hm[4];
+    for (int u0 = u_beg; u0 < u_end; u0 += 256 * kScanUPT) {
+      unsigned hm[kScanUPT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kScanUPT; ++j) {
         const int u = u0 + threadIdx.x + 256 * j;
         hm[j] = u < u_end ? (unsigned)__ldcs(hitmask + (size_t)tile * u_pad + u) : 0u;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kScanUPT; ++j) {
         const int u = u0 + threadIdx.x + 256 * j;
         unsigned hits = hm[j];
         while (hits) {
@@ -635,16 +639,16 @@ k_scan(const uint32_t* __restrict__ gtile, const uint32_t* __restrict__ gmax16, 
     }
     return;
   }
-  for (int u0 = u_beg; u0 < u_end; u0 += 1024) {
-    float thr[4]; uint32_t tw[4];
+  for (int u0 = u_beg; u0 < u_end; u0 += 256 * kScanUPT) {
+    float thr[kScanUPT]; uint32_t tw[kScanUPT];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kScanUPT; ++j) {
       const int u = u0 + threadIdx.x + 256 * j;
       thr[j] = INFINITY; tw[j] = 0xFC00FC00u;          // -inf bounds
       if (u < u_end) { thr[j] = thr_grp[u]; tw[j] = __ldcs(gtile + (size_t)tile * u_pad + u); }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kScanUPT; ++j) {
       const int u = u0 + threadIdx.x + 256 * j;
       const float up = __half2float(__ushort_as_half((unsigned short)(tw[j] >> 16)));
       unsigned hits = 0;
@@ -710,8 +714,11 @@ struct RescoreMeta {          // lanes 0..15 own one user of the step each
   int u; int64_t uid, sb; float thr; int n_seen;
 };
 
+#ifndef LGC_RESCORE_OCC
+#define LGC_RESCORE_OCC 2
+#endif
 template <bool PIPE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, LGC_RESCORE_OCC)
 k_rescore(const int* __restrict__ list, const int* __restrict__ grp_off, int n_tiles, int list_cap, int64_t user0,
           int n_items,
           int d, const float* __restrict__ user_emb, int ld_user, const int64_t* __restrict__ user_ids,
