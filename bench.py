@@ -673,9 +673,19 @@ def bench_c5(args, world, rank, dev, lib, pk):
         e2e_s = float(t.item())
     trainer.use_graph = False
     eager0 = lib.lgc_launch_count()
+    n_tags = 24
+    ms_arr, cnt_arr = (C.c_double * n_tags)(), (C.c_longlong * n_tags)()
+    lib.lgc_profile_enable(1)                # one eager step with CUDA events around every launch of this library
     trainer.step(*dev_triples[0], DECAY)
     torch.cuda.synchronize()
+    lib.lgc_profile_read(ms_arr, cnt_arr, n_tags)
+    lib.lgc_profile_enable(0)
     launches = (lib.lgc_launch_count() - eager0) * args.steps
+    class_ms = {"rows": [round(sum(ms_arr[0:4]), 4), int(sum(cnt_arr[0:4]))],
+                "sweep": [round(sum(ms_arr[4:8]), 4), int(sum(cnt_arr[4:8]))],
+                "finish": [round(sum(ms_arr[8:12]), 4), int(sum(cnt_arr[8:12]))],
+                "bpr": [round(ms_arr[12], 4), int(cnt_arr[12])],
+                "item_exchange": [round(ms_arr[14], 4), int(cnt_arr[14])]}      # [ms, launches] of one eager step
     trainer.use_graph = True
     trainer.check_exchange()
     if rank != 0:
@@ -704,6 +714,7 @@ def bench_c5(args, world, rank, dev, lib, pk):
         "roofline": {"bound": "hbm", "kernel": "whole step, all ranks", "achieved": gbs, "peak": pk["hbm_gbs"] * world,
                      "unit": "GB/s", "frac": gbs / (pk["hbm_gbs"] * world), "traffic": None,
                      "peak_source": pk["source"], "step_algorithmic_bytes": step_bytes,
+                     "class_ms_one_eager_step_rank0": class_ms,
                      "nvlink_bytes_per_step_per_gpu": 2 * layers * n_items * ld * 4 * 2 * (world - 1) // max(world, 1)},
         "parity": info, "cpu_baseline": None, "scoring": None}
     emit(line)

@@ -818,10 +818,12 @@ class BipartiteShardedTrainer(_GraphedStep):
         return self.part.unpad(full)
 
     def weight(self) -> Tensor:
+        self.check_exchange()
         return torch.cat([self._gather_users(self.e0_u), self.e0_i])[:, : self.dim]
 
     def embedding(self) -> Tensor:
         self.propagate()
+        self.check_exchange()
         return torch.cat([self._gather_users(self.out_u), self.out_i])[:, : self.dim]
 
 
