@@ -64,10 +64,13 @@ __device__ __forceinline__ void rows_group(const int2 my, int t0, int n, const f
 // XM: args.x_mask marks the source rows that are not zero; SPLIT: a block's passes are dealt to `split`
 // work items (false: split == 1, the compile-time constant keeps the large-graph code as it was)
 #ifndef LGC_ROWS_OCC
-#define LGC_ROWS_OCC 4
+#define LGC_ROWS_OCC 4          // resident CTAs per SM the compiler must allow: PLAIN epilogues at ld <= 64
+#endif
+#ifndef LGC_ROWS_OCC_WIDE
+#define LGC_ROWS_OCC_WIDE 3     // ADAM / FWD_FINAL epilogues (4-6 operand rows in registers) and wide rows
 #endif
 template <int L, int V, int MODE, bool XM, bool SPLIT>
-__global__ void __launch_bounds__(kRowsThreads, (MODE == EPI_ADAM || MODE == EPI_FWD_FINAL || V > 2) ? 3 : LGC_ROWS_OCC)
+__global__ void __launch_bounds__(kRowsThreads, (MODE == EPI_ADAM || MODE == EPI_FWD_FINAL || V > 2) ? LGC_ROWS_OCC_WIDE : LGC_ROWS_OCC)
 k_spmm_rows(const int32_t* __restrict__ rowptr, const int2* __restrict__ rec, const uint8_t* __restrict__ perm,
             const int32_t* __restrict__ blk_cnt, int n_blocks, int split_arg, int num_rows,
             const float* __restrict__ x, EpiArgs args) {
