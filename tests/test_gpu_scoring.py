@@ -117,6 +117,22 @@ def test_topk_user_subset_and_padded_tables():
     _check_topk(ue[:, :dim], ie[:, :dim], ids, ptr, items, 20, top, sc)
 
 
+def test_result_buffers_can_be_reused():
+    """`out=`: a second call writes into the first call's result tensors (no allocation per call)."""
+    from gnn_ecommerce_b200 import scoring
+    rng = np.random.default_rng(12)
+    ue = torch.from_numpy((rng.standard_normal((700, 64)) * 0.1).astype(np.float32)).to(DEV)
+    ie = torch.from_numpy((rng.standard_normal((5000, 64)) * 0.1).astype(np.float32)).to(DEV)
+    top, sc = scoring.score_topk(ue, ie, None, None, None, 20)
+    want_top, want_sc = top.clone(), sc.clone()
+    top.zero_(); sc.zero_()
+    top2, sc2 = scoring.score_topk(ue, ie, None, None, None, 20, out=(top, sc))
+    assert top2 is top and sc2 is sc
+    assert torch.equal(top, want_top) and torch.equal(sc, want_sc)
+    with pytest.raises(ValueError):
+        scoring.score_topk(ue, ie, None, None, None, 10, out=(top, sc))
+
+
 def test_multiplicative_mask_quirk():
     """Reference `pred * (1 - mask)` (src/lightgcn.py:175): a seen item scores 0.0, not -inf, and
     enters the top-k when the other scores are negative: scores [-1,-2,5,-3] with
