@@ -87,6 +87,7 @@ class PeerArena:
     ALIGN = 256
 
     def __init__(self, capi, lib, nbytes: int, device, group=None):
+        """Allocates this rank's arena only (local, cannot block); `connect()` maps the peers."""
         self._capi, self._lib, self.device, self.group = capi, lib, torch.device(device), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -95,26 +96,31 @@ class PeerArena:
         self.nbytes = (int(nbytes) + self.ALIGN - 1) // self.ALIGN * self.ALIGN + 256      # + control block
         self.ctrl_off = self.nbytes - 256
         self._top = 0
-        base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        base, self._handle = C.c_void_p(), (C.c_ubyte * 64)()
         with torch.cuda.device(self.device):
-            capi.check(lib.lgc_peer_arena_alloc(self.nbytes, C.byref(base), handle), "lgc_peer_arena_alloc")
+            capi.check(lib.lgc_peer_arena_alloc(self.nbytes, C.byref(base), self._handle), "lgc_peer_arena_alloc")
         self.base = int(base.value)
         self.bases, self._opened = [0] * self.world, []
         self.bases[self.rank] = self.base
-        if self.world > 1:
-            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
-            every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(every, mine, group=group)
-            every = every.cpu().numpy().tobytes()
-            with torch.cuda.device(self.device):
-                for q in range(self.world):
-                    if q == self.rank:
-                        continue
-                    peer = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(every[q * 64:(q + 1) * 64])
-                    capi.check(lib.lgc_peer_arena_open(buf, C.byref(peer)), "lgc_peer_arena_open")
-                    self.bases[q] = int(peer.value)
-                    self._opened.append(int(peer.value))
+
+    def connect(self) -> None:
+        """Collective: all-gathers the 64-byte IPC handles and maps every peer's arena. Every rank of the
+        group must call it (the caller makes sure every rank's allocation succeeded first)."""
+        if self.world == 1:
+            return
+        mine = torch.tensor(list(bytes(self._handle)), dtype=torch.uint8, device=self.device)
+        every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        every = every.cpu().numpy().tobytes()
+        with torch.cuda.device(self.device):
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                peer = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(every[q * 64:(q + 1) * 64])
+                self._capi.check(self._lib.lgc_peer_arena_open(buf, C.byref(peer)), "lgc_peer_arena_open")
+                self.bases[q] = int(peer.value)
+                self._opened.append(int(peer.value))
 
     def table(self, rows: int, ld: int) -> Tensor:
         """A zero-filled fp32 `[rows, ld]` table inside the arena (same offset on every rank when every
@@ -655,15 +661,25 @@ class BipartiteShardedTrainer(_GraphedStep):
             if exchange == "peer":
                 raise RuntimeError("exchange='peer' needs 2..8 CUDA ranks and a backend with lgc_item_exchange")
             return None
+        # two collective phases, each agreed on by all ranks before the next starts: a rank that fails must
+        # not leave the others waiting in the all-gather of the handles
+        def all_ok(flag: bool) -> bool:
+            ok = torch.tensor([1 if flag else 0], device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            return int(ok.item()) == 1
+
         arena, err = None, None
         try:
-            arena = self.backend.peer_arena(nbytes, self.dev, self.group)
+            arena = self.backend.peer_arena(nbytes, self.dev, self.group)        # local allocation + IPC export
         except Exception as e:                                   # noqa: BLE001 - reported below, collectively
             err = e
-        ok = torch.tensor([0 if arena is None else 1], device=self.dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-        if int(ok.item()) == 1:
-            return arena
+        if all_ok(arena is not None):
+            try:
+                arena.connect()                                  # all-gather of the handles + peer mappings
+            except Exception as e:                               # noqa: BLE001
+                err = e
+            if all_ok(err is None):
+                return arena
         if arena is not None:
             arena.close()
         if exchange == "peer":
