@@ -14,6 +14,10 @@ gradient table is never communicated. Layout trick: shards are padded to a commo
 `max_rows` and sources are renumbered to `owner * max_rows + local`, so the all-gather output IS
 the gather table of the next layer (no re-packing, equal-sized NCCL chunks).
 
+`BipartiteShardedTrainer` (the default for the reference's user-item graphs) shards the USERS
+instead, replicates the small item table and exchanges only the item rows, through a hand-written
+peer-memory kernel (`PeerArena`, `lgc_item_exchange`) or NCCL -- see its docstring.
+
 The arithmetic is the same sm_100a kernels (`lgc_spmm_ex`, `lgc_bpr_loss_grad`) through the C ABI;
 a `backend` object carries those calls so the orchestration can be exercised on CPU with `gloo`
 (tests inject a checker backend; the product backend is `CudaBackend` and has no fallback).
@@ -524,11 +528,15 @@ class BipartiteShardedTrainer(_GraphedStep):
     all-gather of whole tables): USERS are partitioned over the ranks (balanced by in-degree + 4),
     the small ITEM table is replicated. Per layer a rank computes its users' rows from the replicated
     item table (rows kernel, fused epilogue, no communication) and the PARTIAL sums of every item row
-    over its own users (sweep kernel); one all-reduce of the `[n_items, ld]` partials completes the
-    item rows, whose (replicated) epilogue is ONE launch of the same fused epilogue
-    (`lgc_epilogue_apply`). The all-reduce of layer l runs on NCCL's stream while the rank computes its
-    user rows of layer l and the item partials of layer l + 1. Item-row sums are reduced in a
-    different order than on one GPU: equal within fp32 tolerance, not bit-exact.
+    over its own users (sweep kernel). The item rows are completed by `lgc_item_exchange`
+    (`csrc/exchange.cu`, `exchange="peer"`): ONE kernel per rank and layer over NVLink peer memory that
+    sums a row slice over all ranks' partial tables (P2P loads, fixed rank order), applies the item
+    rows' fused epilogue and stores the results into every rank's replica (P2P stores) -- or, with
+    `exchange="nccl"`, by an asynchronous `ncclAllReduce` of the `[n_items, ld]` partials followed by
+    one launch of the same epilogue (`lgc_epilogue_apply`) on every rank. Either way the exchange of
+    layer l runs on a side stream while the rank computes its user rows of layer l and the item
+    partials of layer l + 1. Item-row sums are reduced in a different order than on one GPU: equal
+    within fp32 tolerance, not bit-exact (the two exchange paths agree bit for bit at two ranks).
 
     A rank needs only ITS OWN users' interactions: the two rectangular operators are built from that
     slice (`from_pairs`), the item degrees are the all-reduced partial degrees, so no process ever
