@@ -663,7 +663,9 @@ class BipartiteShardedTrainer(_GraphedStep):
             exchange = os.environ.get("LGC_EXCHANGE", "auto")
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
-        able = (exchange != "nccl" and self.world > 1 and self.world <= 8 and self.dev.type == "cuda"
+        # (`peer_on_cpu`: only the CPU test double sets it, to drive the collective agreement below under gloo)
+        able = (exchange != "nccl" and self.world > 1 and self.world <= 8
+                and (self.dev.type == "cuda" or bool(getattr(self.backend, "peer_on_cpu", False)))
                 and bool(getattr(self.backend, "supports_peer", False)))
         if not able:
             if exchange == "peer":

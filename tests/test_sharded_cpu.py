@@ -88,6 +88,70 @@ def test_sharded_step_matches_reference(world, mode, tmp_path):
     assert b[-1] == (want_w.shape[0] if mode == "rows" else 600)
 
 
+class _FailingArena:
+    """What `CudaBackend.peer_arena` returns, reduced to the two collective steps and their failure modes."""
+    closed = 0
+
+    def __init__(self, fail_connect):
+        self._fail_connect = fail_connect
+
+    def connect(self):
+        dist.barrier()                                   # the all-gather of the handles: every rank must get here
+        if self._fail_connect:
+            raise RuntimeError("cudaIpcOpenMemHandle: peer access is not supported between these two devices")
+
+    def close(self):
+        _FailingArena.closed += 1
+
+
+def _fallback_worker(rank, world, port_no, out, fail_at):
+    import warnings
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _cpu_backend import CpuCheckBackend
+    from gnn_ecommerce_b200.sharded import make_sharded_trainer
+
+    class Backend(CpuCheckBackend):
+        supports_peer, peer_on_cpu = True, True
+
+        def peer_arena(self, nbytes, device, group):
+            if fail_at == "alloc" and rank == 1:
+                raise RuntimeError("cudaMalloc: out of memory")
+            return _FailingArena(fail_at == "connect" and rank == 0)
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
+    g, ei, ew, init, triples = _inputs()
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        tr = make_sharded_trainer(ei, ew, g.num_nodes, DIM, LAYERS, init, mode="bipartite", lr=LR, backend=Backend(),
+                                  ld=DIM)
+    # every rank fell back together (no rank is left waiting in a collective), arenas that did get made are closed
+    assert tr.peer is None
+    assert any("ncclAllReduce" in str(w.message) for w in caught)
+    assert _FailingArena.closed == (0 if (fail_at == "alloc" and rank == 1) else 1)
+    losses = [tr.step(*t, DECAY).numpy() for t in triples]
+    if rank == 0:
+        torch.save({"losses": np.array(losses)}, out)
+    # exchange="peer" must raise on every rank instead of falling back
+    with pytest.raises(RuntimeError):
+        make_sharded_trainer(ei, ew, g.num_nodes, DIM, LAYERS, init, mode="bipartite", lr=LR, backend=Backend(),
+                             ld=DIM, exchange="peer")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_at", ["alloc", "connect"])
+def test_peer_arena_failure_on_one_rank_falls_back_on_all(fail_at, tmp_path):
+    """The peer-memory exchange is set up in two collective phases (`_open_peer_arena`): if one rank cannot
+    allocate or map an arena, ALL ranks must agree to use the NCCL path -- none may hang in the all-gather of
+    the IPC handles -- and the step must still match the reference."""
+    out = str(tmp_path / "res.pt")
+    port_no = 31500 + (os.getpid() % 2000) + (1 if fail_at == "connect" else 0)
+    mp.spawn(_fallback_worker, args=(2, port_no, out, fail_at), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    want_losses, _, _ = _reference()
+    assert np.allclose(got["losses"], want_losses, rtol=1e-5, atol=0)
+
+
 def test_bipartite_split_detection():
     from gnn_ecommerce_b200.sharded import bipartite_split
     _, ei, _, _, _ = _inputs()
