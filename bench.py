@@ -734,10 +734,13 @@ def finish(world, trainer):
     if world > 1:
         import torch
         import torch.distributed as dist
-        if hasattr(trainer, "close"):
-            trainer.close()
-        elif hasattr(trainer, "release_graph"):
-            trainer.release_graph()
+        try:
+            if hasattr(trainer, "close"):
+                trainer.close()
+            elif hasattr(trainer, "release_graph"):
+                trainer.release_graph()
+        except Exception as e:            # teardown must not turn a measured run into a failed one
+            log(f"[bench] teardown: {e!r}")
         torch.cuda.synchronize()
         dist.barrier()
         sys.stderr.flush()

@@ -706,13 +706,24 @@ class BipartiteShardedTrainer(_GraphedStep):
                 raise RuntimeError(f"lgc_item_exchange: a peer did not arrive in time (phase {err}); results invalid")
 
     def close(self) -> None:
-        """Collective teardown of the peer arenas (call on every rank before destroying the process group)."""
+        """Collective teardown of the peer arenas (call on every rank before destroying the process group).
+        The item tables live inside the arena: they are moved to ordinary tensors first, so `weight()` and
+        `embedding()` (through the NCCL path) stay valid afterwards; `step()` does not -- with the peer
+        exchange the Adam moments of the item rows are sharded by row slice, not replicated."""
         self.release_graph()
         if getattr(self, "peer", None) is not None:
-            torch.cuda.synchronize(self.dev)
-            dist.barrier(group=self.group)
+            if self.dev.type == "cuda":
+                torch.cuda.synchronize(self.dev)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)               # nobody reads or writes any arena after this point
+            for name in ("e0_i", "m_i", "v_i", "out_i"):
+                setattr(self, name, getattr(self, name).clone())
+            self.xi = [t.clone() for t in self.xi]
+            self.part_i = [t.clone() for t in self.part_i]
+            if self.dev.type == "cuda":
+                torch.cuda.synchronize(self.dev)
             self.peer.close()
-            self.peer = None
+            self.peer, self._side, self._closed = None, None, True
 
     def __del__(self):
         for name in ("gu", "gi"):
@@ -787,6 +798,8 @@ class BipartiteShardedTrainer(_GraphedStep):
 
     # ------------------------------------------------------------------ one mini-batch
     def _step_impl(self, users: Tensor, pos: Tensor, neg: Tensor, decay: float) -> Tensor:
+        if getattr(self, "_closed", False):
+            raise RuntimeError("the trainer was closed (its peer arenas are gone): build a new one to keep training")
         b, a, K, ld, s = self.backend, self.alpha, self.layers, self.ld, self.n_users
         batch = users.numel()
         self.propagate()

@@ -152,6 +152,35 @@ def test_peer_arena_failure_on_one_rank_falls_back_on_all(fail_at, tmp_path):
     assert np.allclose(got["losses"], want_losses, rtol=1e-5, atol=0)
 
 
+def test_close_moves_the_item_tables_out_of_the_arena():
+    """`close()` frees the peer arena the item tables live in: they must be ordinary tensors afterwards
+    (no use after free in `weight()` / `embedding()`), and `step()` must refuse to continue."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _cpu_backend import CpuCheckBackend
+    from gnn_ecommerce_b200.sharded import make_sharded_trainer
+    g, ei, ew, init, triples = _inputs()
+    tr = make_sharded_trainer(ei, ew, g.num_nodes, DIM, LAYERS, init, mode="bipartite", lr=LR, backend=CpuCheckBackend(),
+                              ld=DIM)
+    tr.step(*triples[0], DECAY)
+    w, emb = tr.weight().clone(), tr.embedding().clone()
+
+    class Arena:                                         # stands for the CUDA IPC arena
+        closed = False
+
+        def close(self):
+            Arena.closed = True
+    before = {n: getattr(tr, n) for n in ("e0_i", "m_i", "v_i", "out_i")}
+    tr.peer = Arena()
+    tr.close()
+    assert Arena.closed and tr.peer is None
+    for n, t in before.items():
+        now = getattr(tr, n)
+        assert now is not t and now.data_ptr() != t.data_ptr() and torch.equal(now, t)
+    assert torch.equal(tr.weight(), w) and torch.allclose(tr.embedding(), emb)
+    with pytest.raises(RuntimeError, match="closed"):
+        tr.step(*triples[1], DECAY)
+
+
 def test_bipartite_split_detection():
     from gnn_ecommerce_b200.sharded import bipartite_split
     _, ei, _, _, _ = _inputs()
