@@ -870,11 +870,13 @@ def make_sharded_trainer(edge_index: Tensor, edge_weight: Optional[Tensor], num_
                          num_layers: int, init_weight: Tensor, mode: str = "auto", **kw):
     """`mode`: "bipartite" (users sharded, items replicated + all-reduced), "rows" (destination rows
     partitioned, all-gather per layer -- works for any symmetric graph) or "auto" (bipartite when the
-    edge list has the users-then-items layout)."""
+    edge list has the users-then-items layout). `exchange` ("auto" | "peer" | "nccl", bipartite only): how the
+    item rows are completed per layer -- see `BipartiteShardedTrainer`."""
     s = bipartite_split(edge_index) if mode in ("auto", "bipartite") else None
     if mode == "bipartite" and s is None:
         raise ValueError("edge_index is not bipartite with users numbered before items")
     if s is not None:
         return BipartiteShardedTrainer(edge_index, edge_weight, num_nodes, embedding_dim, num_layers, init_weight,
                                        n_users=s, **kw)
+    kw.pop("exchange", None)              # only the bipartite trainer has item rows to exchange
     return ShardedBPRTrainer(edge_index, edge_weight, num_nodes, embedding_dim, num_layers, init_weight, **kw)
